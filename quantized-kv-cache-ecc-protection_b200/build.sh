@@ -1,0 +1,7 @@
+#!/bin/sh
+# Build libeccq_sm100a.so in-tree (sm_100a only). Usage: sh build.sh [extra nvcc flags]
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+mkdir -p "$HERE/lib"
+exec nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared \
+  -I"$HERE/../include" -I"$HERE/csrc" "$@" "$HERE/csrc/eccq_lib.cu" -o "$HERE/lib/libeccq_sm100a.so"

@@ -1,0 +1,362 @@
+// eccq_attention.cu -- ECC-fused paged decode attention (q_len == 1), split over the context (FlashDecoding).
+//
+// Replaces paged_attention_ecc / paged_attention_ecc_kernel (kv_cache/attention_ecc.py:620-780, :264-426): the reference
+// walks the whole context serially with one program per (batch, q-head), re-decoding every K/V row once per q-head
+// and mis-indexing GQA caches.  Here one CTA owns a (sequence, kv-head, context-chunk): it decodes each
+// codeword row once for the whole GQA group, keeps an online-softmax state per q-head and writes a partial
+// (m, l, acc); a second small kernel merges the chunks.  Codeword bytes are consumed directly: the Hamming syndrome
+// decode (or the Golay table decode) is the K/V prologue, per-token scales are applied to the score / to P.
+//
+// v0 (this file): CUDA-core dot products, warp per token.  The tcgen05/TMEM tile version builds on the same
+// partial/merge protocol.
+#include "eccq_internal.h"
+
+namespace eccq {
+
+struct AttnArgs {
+  const void* q;
+  void* out;
+  const int32_t* block_table;
+  const int32_t* context_lens;
+  float* ws;        // [nseq, Hq, nsplit, D + 2]  (acc[D], m, l)
+  int max_blocks, nseq, Hq, layer, nsplit, chunk;
+  float sm_scale;
+  int interp, v_use_k_scales, count_errors;
+};
+
+constexpr int kAttnThreads = 256;
+constexpr int kAttnWarps = kAttnThreads / 32;
+
+template <typename T>
+__device__ __forceinline__ float ldq(const void* q, int64_t i) { return Cvt<T>::from(reinterpret_cast<const T*>(q)[i]); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// EPL = values per lane. Hamming/int4: EPL = 4*NCH (one 32-bit word of codeword bytes per 128-value chunk);
+// Golay: EPL = 3*NIT (one codeword per 32-codeword sweep).
+template <typename TQ, int CODEC, int GP, int NCH>
+__global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g, AttnArgs a, uint64_t* counters) {
+  constexpr bool GOLAY = CODEC == ECCQ_CODEC_GOLAY;
+  constexpr int VPC = GOLAY ? 3 : 4;   // values per lane per chunk
+  constexpr int EPL = VPC * NCH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: [golay tables] q[GP][EPL*32] floats, then per-warp merge area
+  uint16_t* s_lo = nullptr; uint16_t* s_hi = nullptr; int32_t* s_syn = nullptr;
+  unsigned char* p = smem_raw;
+  if (GOLAY) {
+    s_syn = reinterpret_cast<int32_t*>(p); p += 4096 * 4;
+    s_lo = reinterpret_cast<uint16_t*>(p); p += 128;
+    s_hi = reinterpret_cast<uint16_t*>(p); p += 128;
+    golay_load_parity(s_lo, s_hi);
+    golay_load_syndrome(s_syn);
+  }
+  float* s_red = reinterpret_cast<float*>(p);  // [kAttnWarps][GP][EPL*32 + 2]
+
+  const int split = blockIdx.x;
+  const int G = a.Hq / g.H;
+  const int npass = (G + GP - 1) / GP;
+  const int h = blockIdx.y / npass;
+  const int pass = blockIdx.y - h * npass;
+  const int i = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ctx = a.context_lens[i];
+  const int c0 = split * a.chunk;
+  const int c1 = min(ctx, c0 + a.chunk);
+  const int g0 = pass * GP;                 // first q-head (within the group) of this pass
+  const int ng = min(GP, G - g0);
+  const int32_t* bt = a.block_table + (int64_t)i * a.max_blocks;
+  const int rowbytes = GOLAY ? g.cw * 4 : g.D;
+  const int64_t page_bytes = (int64_t)g.bs * rowbytes;
+
+  // element index of value v (0..VPC-1) of chunk ch for this lane, or -1
+  auto elem = [&](int ch, int v) -> int {
+    const int e = GOLAY ? 3 * (ch * 32 + lane) + v : ch * 128 + lane * 4 + v;
+    return e < g.D ? e : -1;
+  };
+
+  // q for this lane: qreg[gi][ch*VPC+v], pre-multiplied by sm_scale
+  float qreg[GP][EPL];
+#pragma unroll
+  for (int gi = 0; gi < GP; ++gi)
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int v = 0; v < VPC; ++v) {
+        const int e = elem(ch, v);
+        qreg[gi][ch * VPC + v] = (gi < ng && e >= 0) ? ldq<TQ>(a.q, ((int64_t)i * a.Hq + (int64_t)h * G + g0 + gi) * g.D + e) * a.sm_scale : 0.0f;
+      }
+  if (GOLAY) __syncthreads();
+
+  float m[GP], l[GP], acc[GP][EPL];
+#pragma unroll
+  for (int gi = 0; gi < GP; ++gi) {
+    m[gi] = -INFINITY; l[gi] = 0.0f;
+#pragma unroll
+    for (int x = 0; x < EPL; ++x) acc[gi][x] = 0.0f;
+  }
+  uint32_t ncorr = 0, ndet = 0;
+  const bool do_count = a.count_errors && pass == 0;
+
+  // decode the values this lane owns of token `tok` from `cache`; returns false if the token has no block
+  auto decode_row = [&](const uint8_t* cache, int tok, float (&val)[EPL], uint32_t (&dbl)[NCH], bool count, int& blk_out, int& slot_out) -> bool {
+    const int lb = tok / g.bs, slot = tok - lb * g.bs;
+    const int blk = bt[lb];
+    blk_out = blk; slot_out = slot;
+    if (blk < 0) return false;
+    const uint8_t* row = cache + page_index(g, blk, a.layer, h) * page_bytes + (int64_t)slot * rowbytes;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      dbl[ch] = 0;
+      if (GOLAY) {
+        const int j = ch * 32 + lane;
+        uint32_t d = 0;
+        if (j < g.cw) {
+          uint32_t cnt;
+          d = golay_decode1(s_lo, s_hi, s_syn, __ldg(reinterpret_cast<const uint32_t*>(row) + j), cnt);
+          if (count) { if (cnt == 4u) ++ndet; else ncorr += cnt; }
+        }
+        val[ch * 3] = (float)(int)(d & 0xF) - 8.0f;
+        val[ch * 3 + 1] = (float)(int)((d >> 4) & 0xF) - 8.0f;
+        val[ch * 3 + 2] = (float)(int)((d >> 8) & 0xF) - 8.0f;
+      } else {
+        const int e0 = ch * 128 + lane * 4;
+        uint32_t nib = 0x08080808u;
+        if (e0 < g.D) {
+          const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(row + e0));
+          if (CODEC == ECCQ_CODEC_H84) {
+            const Dec4 d = h84_decode4(w);
+            nib = d.nib; dbl[ch] = h84_double4(d);
+            if (count) { ncorr += __popc(h84_single4(d)); ndet += __popc(dbl[ch]); }
+          } else if (CODEC == ECCQ_CODEC_H74) {
+            const Dec4 d = h74_decode4(w);
+            nib = d.nib;
+            if (count) ncorr += __popc(d.nz);
+          } else {
+            nib = w;
+          }
+        }
+        // stash the nibble word in val[] bit patterns until interpolation is resolved
+        val[ch * 4] = __uint_as_float(nib);
+      }
+    }
+    return true;
+  };
+  // Hamming: nibble word of a neighbour token for chunk ch (pre-interpolation decode)
+  auto neighbour_word = [&](const uint8_t* cache, int tok, int ch) -> uint32_t {
+    const int lb = tok / g.bs, slot = tok - lb * g.bs;
+    const int blk = bt[lb];
+    if (blk < 0) return 0u;
+    const uint8_t* row = cache + page_index(g, blk, a.layer, h) * page_bytes + (int64_t)slot * rowbytes;
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(row + ch * 128 + lane * 4));
+    return h84_decode4(w).nib;
+  };
+  auto finish_row = [&](const uint8_t* cache, int tok, float (&val)[EPL], const uint32_t (&dbl)[NCH]) {
+    if constexpr (!GOLAY) {
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      uint32_t nib = __float_as_uint(val[ch * 4]);
+      if (CODEC == ECCQ_CODEC_H84 && a.interp && dbl[ch]) {
+        const uint32_t left = tok > 0 ? neighbour_word(cache, tok - 1, ch) : nib;
+        const uint32_t right = tok + 1 < ctx ? neighbour_word(cache, tok + 1, ch) : nib;
+        nib = interp4(nib, left, right, dbl[ch]);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) val[ch * 4 + v] = byte_to_float_m8(nib, v);
+    }
+    }
+  };
+
+  for (int tok = c0 + warp; tok < c1; tok += kAttnWarps) {
+    float kv[EPL];
+    uint32_t dbl[NCH];
+    int blk, slot;
+    if (!decode_row(g.k_cache, tok, kv, dbl, do_count, blk, slot)) continue;
+    finish_row(g.k_cache, tok, kv, dbl);
+    const int64_t sidx = page_index(g, blk, a.layer, h) * g.bs + slot;
+    const float ksc = __ldg(g.k_scales + sidx);
+    const float vsc = a.v_use_k_scales ? ksc : __ldg(g.v_scales + sidx);
+    float s[GP];
+#pragma unroll
+    for (int gi = 0; gi < GP; ++gi) {
+      float d = 0.0f;
+#pragma unroll
+      for (int x = 0; x < EPL; ++x) d = fmaf(qreg[gi][x], kv[x], d);
+      s[gi] = warp_sum(d) * ksc;
+    }
+    float vv[EPL];
+    decode_row(g.v_cache, tok, vv, dbl, do_count, blk, slot);
+    finish_row(g.v_cache, tok, vv, dbl);
+#pragma unroll
+    for (int gi = 0; gi < GP; ++gi) {
+      const float mn = fmaxf(m[gi], s[gi]);
+      const float alpha = __expf(m[gi] - mn);   // exp(-inf) = 0 on the first token
+      const float pw = __expf(s[gi] - mn);
+      l[gi] = l[gi] * alpha + pw;
+      const float pv = pw * vsc;
+#pragma unroll
+      for (int x = 0; x < EPL; ++x) acc[gi][x] = fmaf(acc[gi][x], alpha, pv * vv[x]);
+      m[gi] = mn;
+    }
+  }
+
+  // ---- merge the warps of this CTA through shared memory, write the chunk partial
+  constexpr int RS = EPL * 32 + 2;
+#pragma unroll
+  for (int gi = 0; gi < GP; ++gi) {
+    float* dst = s_red + ((size_t)warp * GP + gi) * RS;
+#pragma unroll
+    for (int x = 0; x < EPL; ++x) dst[x * 32 + lane] = acc[gi][x];
+    if (lane == 0) { dst[EPL * 32] = m[gi]; dst[EPL * 32 + 1] = l[gi]; }
+  }
+  __syncthreads();
+  for (int gi = warp; gi < ng; gi += kAttnWarps) {
+    float M = -INFINITY;
+    for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, s_red[((size_t)w * GP + gi) * RS + EPL * 32]);
+    float Lsum = 0.0f, o[EPL];
+#pragma unroll
+    for (int x = 0; x < EPL; ++x) o[x] = 0.0f;
+    for (int w = 0; w < kAttnWarps; ++w) {
+      const float* src = s_red + ((size_t)w * GP + gi) * RS;
+      const float mw = src[EPL * 32];
+      const float f = (mw == -INFINITY) ? 0.0f : __expf(mw - M);
+      Lsum += src[EPL * 32 + 1] * f;
+#pragma unroll
+      for (int x = 0; x < EPL; ++x) o[x] += src[x * 32 + lane] * f;
+    }
+    const int qh = h * G + g0 + gi;
+    float* wsrow = a.ws + (((int64_t)i * a.Hq + qh) * a.nsplit + split) * (g.D + 2);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int v = 0; v < VPC; ++v) {
+        const int e = elem(ch, v);
+        if (e >= 0) wsrow[e] = o[ch * VPC + v];
+      }
+    if (lane == 0) { wsrow[g.D] = M; wsrow[g.D + 1] = Lsum; }
+  }
+  if (a.count_errors) {
+    const int idx[2] = {ECCQ_CTR_CORRECTED, ECCQ_CTR_DETECTED};
+    const uint32_t val[2] = {ncorr, ndet};
+    block_accumulate<2>(counters, idx, val);
+  }
+}
+
+// out[i, qh, :] = sum_s acc_s * exp(m_s - M) / sum_s l_s * exp(m_s - M); empty context -> zeros
+template <typename TQ>
+__global__ void attn_merge_kernel(const float* __restrict__ ws, TQ* __restrict__ out, int Hq, int D, int nsplit) {
+  const int qh = blockIdx.x, i = blockIdx.y;
+  const float* base = ws + ((int64_t)i * Hq + qh) * nsplit * (D + 2);
+  float M = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, base[(int64_t)s * (D + 2) + D]);
+  for (int e = threadIdx.x; e < D; e += blockDim.x) {
+    float num = 0.0f, den = 0.0f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float* r = base + (int64_t)s * (D + 2);
+      const float f = (r[D] == -INFINITY) ? 0.0f : __expf(r[D] - M);
+      num += r[e] * f;
+      den += r[D + 1] * f;
+    }
+    out[((int64_t)i * Hq + qh) * D + e] = Cvt<TQ>::to(den > 0.0f ? num / den : 0.0f);
+  }
+}
+
+static inline void attn_plan(int max_context, int& nsplit, int& chunk) {
+  chunk = 256;
+  nsplit = (max_context + chunk - 1) / chunk;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > 128) { nsplit = 128; chunk = ((max_context + nsplit - 1) / nsplit + 15) / 16 * 16; }
+}
+
+template <typename TQ, int CODEC, int GP, int NCH>
+static int launch_attn(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  constexpr int VPC = CODEC == ECCQ_CODEC_GOLAY ? 3 : 4;
+  const size_t smem = (CODEC == ECCQ_CODEC_GOLAY ? 4096 * 4 + 256 : 0) + sizeof(float) * kAttnWarps * GP * (VPC * NCH * 32 + 2);
+  auto kern = attn_partial_kernel<TQ, CODEC, GP, NCH>;
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
+  }
+  const int G = a.Hq / g.H;
+  const int npass = (G + GP - 1) / GP;
+  dim3 grid(a.nsplit, g.H * npass, a.nseq);
+  kern<<<grid, kAttnThreads, smem, st>>>(g, a, counters);
+  return ECCQ_OK;
+}
+
+template <typename TQ, int CODEC>
+static int dispatch_attn(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  const int G = a.Hq / g.H;
+  const int per_chunk = CODEC == ECCQ_CODEC_GOLAY ? 96 : 128;
+  const int nch = (g.D + per_chunk - 1) / per_chunk;
+  if (nch > 2) return fail(ECCQ_EUNSUPPORTED, "paged_decode_attention: head_dim too large");
+#define ECCQ_ATTN_CASE(GPV)                                                                           \
+  return nch == 1 ? launch_attn<TQ, CODEC, GPV, 1>(g, a, counters, st) : launch_attn<TQ, CODEC, GPV, 2>(g, a, counters, st)
+  if (G == 1) { ECCQ_ATTN_CASE(1); }
+  if (G == 2) { ECCQ_ATTN_CASE(2); }
+  if (G <= 4) { ECCQ_ATTN_CASE(4); }
+  ECCQ_ATTN_CASE(8);
+#undef ECCQ_ATTN_CASE
+}
+
+template <typename TQ>
+static int run_attn(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  int rc;
+  switch (g.codec) {
+    case ECCQ_CODEC_H74: rc = dispatch_attn<TQ, ECCQ_CODEC_H74>(g, a, counters, st); break;
+    case ECCQ_CODEC_H84: rc = dispatch_attn<TQ, ECCQ_CODEC_H84>(g, a, counters, st); break;
+    case ECCQ_CODEC_GOLAY: rc = dispatch_attn<TQ, ECCQ_CODEC_GOLAY>(g, a, counters, st); break;
+    default: rc = dispatch_attn<TQ, ECCQ_CODEC_INT4>(g, a, counters, st); break;
+  }
+  if (rc) return rc;
+  dim3 mg(a.Hq, a.nseq);
+  attn_merge_kernel<TQ><<<mg, 128, 0, st>>>(a.ws, reinterpret_cast<TQ*>(a.out), a.Hq, g.D, a.nsplit);
+  return ECCQ_OK;
+}
+
+}  // namespace eccq
+
+using namespace eccq;
+
+extern "C" int64_t eccq_attention_workspace_bytes(int nseq, int Hq, int D, int max_context) {
+  if (nseq <= 0 || Hq <= 0 || D <= 0) return 0;
+  int nsplit, chunk;
+  attn_plan(max_context, nsplit, chunk);
+  return (int64_t)nseq * Hq * nsplit * (D + 2) * (int64_t)sizeof(float);
+}
+
+extern "C" int eccq_paged_decode_attention(const eccq_cache_desc* c, const void* q, void* out, int q_dtype,
+                                           const int32_t* block_table, int max_blocks, const int32_t* context_lens, int nseq,
+                                           int Hq, int layer, float sm_scale, int use_interpolation, int v_use_k_scales,
+                                           int count_errors, void* workspace, int64_t workspace_bytes, uint64_t* counters,
+                                           void* stream) {
+  CacheGeom g;
+  if (!make_geom(c, g)) return fail(ECCQ_EINVAL, "paged_decode_attention: bad cache descriptor");
+  if (nseq < 0 || Hq <= 0 || Hq % g.H != 0 || layer < 0 || layer >= g.L || max_blocks <= 0 || !block_table || !context_lens)
+    return fail(ECCQ_EINVAL, "paged_decode_attention: bad arguments");
+  if (nseq == 0) return ECCQ_OK;
+  if (!q || !out || !workspace) return fail(ECCQ_EINVAL, "paged_decode_attention: null pointer");
+  if (g.codec != ECCQ_CODEC_GOLAY && (g.D % 4 != 0 || (reinterpret_cast<uintptr_t>(g.k_cache) & 3) || (reinterpret_cast<uintptr_t>(g.v_cache) & 3)))
+    return fail(ECCQ_EUNSUPPORTED, "paged_decode_attention: head_dim must be a multiple of 4 for byte codecs");
+  if (int rc = ensure_tables()) return rc;
+  AttnArgs a;
+  a.q = q; a.out = out; a.block_table = block_table; a.context_lens = context_lens; a.ws = (float*)workspace;
+  a.max_blocks = max_blocks; a.nseq = nseq; a.Hq = Hq; a.layer = layer; a.sm_scale = sm_scale;
+  a.interp = use_interpolation && g.codec == ECCQ_CODEC_H84; a.v_use_k_scales = v_use_k_scales; a.count_errors = count_errors && counters;
+  attn_plan(max_blocks * g.bs, a.nsplit, a.chunk);
+  if (workspace_bytes < (int64_t)nseq * Hq * a.nsplit * (g.D + 2) * (int64_t)sizeof(float))
+    return fail(ECCQ_EINVAL, "paged_decode_attention: workspace too small (size it with max_context = max_blocks*block_size)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  switch (q_dtype) {
+    case ECCQ_F32: rc = run_attn<float>(g, a, counters, st); break;
+    case ECCQ_F16: rc = run_attn<__half>(g, a, counters, st); break;
+    case ECCQ_BF16: rc = run_attn<__nv_bfloat16>(g, a, counters, st); break;
+    default: return fail(ECCQ_EINVAL, "paged_decode_attention: bad dtype");
+  }
+  if (rc) return rc;
+  return check_launch("paged_decode_attention");
+}

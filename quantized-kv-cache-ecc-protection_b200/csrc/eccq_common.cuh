@@ -1,0 +1,288 @@
+// eccq_common.cuh -- device-side building blocks shared by every kernel of libeccq_sm100a.so.
+//
+// All codec arithmetic is SWAR ("SIMD within a register"): four codeword bytes ride in one 32-bit lane and the
+// 8-entry Hamming syndrome table of the reference (ecc_codecs/triton_kernels/config.py:131-161) is folded into
+// LOP3 boolean logic, so the "table" lives in the instruction stream / registers and nothing is gathered.
+// The Golay tables (2 x 64-entry parity split table, 4096-entry syndrome table) live in shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "eccq.h"
+
+namespace eccq {
+
+constexpr uint32_t M01 = 0x01010101u;
+constexpr uint32_t M0F = 0x0F0F0F0Fu;
+
+// ------------------------------------------------------------------------------------------------ memory
+__device__ __forceinline__ uint4 ld_stream(const void* p) { return __ldcs(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void st_stream(void* p, uint4 v) { __stcs(reinterpret_cast<uint4*>(p), v); }
+__device__ __forceinline__ uint2 ld_stream8(const void* p) { return __ldcs(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ void st_stream8(void* p, uint2 v) { __stcs(reinterpret_cast<uint2*>(p), v); }
+
+__host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// One atomicAdd per CTA per counter: lanes -> warp (redux) -> shared -> global.
+template <int NV>
+__device__ __forceinline__ void block_accumulate(uint64_t* counters, const int (&idx)[NV], const uint32_t (&val)[NV]) {
+  __shared__ uint32_t s_acc[NV];
+  if (threadIdx.x < NV) s_acc[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    uint32_t w = __reduce_add_sync(0xFFFFFFFFu, val[i]);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_acc[i], w);
+  }
+  __syncthreads();
+  if (counters != nullptr && threadIdx.x < NV && s_acc[threadIdx.x])
+    atomicAdd(reinterpret_cast<unsigned long long*>(counters) + idx[threadIdx.x], (unsigned long long)s_acc[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------ Hamming, 4 bytes/lane
+// Encode: parity equations of hamming74_triton.py:62-72 / hamming84_triton.py:83-106 on the low nibble of each byte.
+__device__ __forceinline__ uint32_t h74_encode4(uint32_t x) {
+  x &= M0F;
+  const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
+  const uint32_t p0 = (x ^ x1 ^ x3) & M01;   // d0^d1^d3
+  const uint32_t p1 = (x ^ x2 ^ x3) & M01;   // d0^d2^d3
+  const uint32_t p2 = (x1 ^ x2 ^ x3) & M01;  // d1^d2^d3
+  return x | (p0 << 4) | (p1 << 5) | (p2 << 6);
+}
+__device__ __forceinline__ uint32_t h84_encode4(uint32_t x) {
+  x &= M0F;
+  const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3;
+  const uint32_t p0 = (x ^ x1 ^ x3) & M01;
+  const uint32_t p1 = (x ^ x2 ^ x3) & M01;
+  const uint32_t p2 = (x1 ^ x2 ^ x3) & M01;
+  // overall parity of the 7 Hamming bits: p0^p1^p2 == d3, so it collapses to d0^d1^d2
+  const uint32_t po = (x ^ x1 ^ x2) & M01;
+  return x | (p0 << 4) | (p1 << 5) | (p2 << 6) | (po << 7);
+}
+
+struct Dec4 {
+  uint32_t nib;  // corrected nibbles, one per byte
+  uint32_t nz;   // 0x01 per byte: syndrome != 0
+  uint32_t pe;   // 0x01 per byte: overall-parity mismatch (Hamming(8,4) only)
+};
+
+// Syndrome bits of hamming84_triton.py:160-164; the LUT [-1,4,5,0,6,1,2,3] only touches a DATA bit for syndromes
+// 3,5,6,7 (bits 0,1,2,3), which is all the decoded nibble can see, so the correction is four AND terms.
+__device__ __forceinline__ Dec4 h84_decode4(uint32_t x) {
+  const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3, x4 = x >> 4, x5 = x >> 5, x6 = x >> 6;
+  const uint32_t s0 = (x ^ x1 ^ x3 ^ x4) & M01;
+  const uint32_t s1 = (x ^ x2 ^ x3 ^ x5) & M01;
+  const uint32_t s2 = (x1 ^ x2 ^ x3 ^ x6) & M01;
+  uint32_t t = x ^ x4;  // fold all 8 bits: stored parity vs recomputed parity
+  t ^= t >> 2;
+  t ^= t >> 1;
+  const uint32_t pe = t & M01;
+  const uint32_t s0p = s0 & pe;                 // only type 1 (syndrome!=0 & parity error) is corrected
+  const uint32_t f0 = s0p & s1 & ~s2;           // syndrome 3 -> d0
+  const uint32_t f1 = s0p & ~s1 & s2;           // syndrome 5 -> d1
+  const uint32_t f2 = ~s0 & s1 & s2 & pe;       // syndrome 6 -> d2
+  const uint32_t f3 = s0p & s1 & s2;            // syndrome 7 -> d3
+  Dec4 r;
+  r.nib = (x & M0F) ^ (f0 | (f1 << 1) | (f2 << 2) | (f3 << 3));
+  r.nz = s0 | s1 | s2;
+  r.pe = pe;
+  return r;
+}
+// error type byte of hamming84_triton.py:185-187: 0 none, 1 single corrected, 2 double detected, 3 parity only
+__device__ __forceinline__ uint32_t h84_etype4(const Dec4& d) { return d.pe | ((d.nz ^ d.pe) << 1); }
+__device__ __forceinline__ uint32_t h84_single4(const Dec4& d) { return d.nz & d.pe; }
+__device__ __forceinline__ uint32_t h84_double4(const Dec4& d) { return d.nz & ~d.pe; }
+
+// hamming74_triton.py:129-160: bit 7 is ignored, every non-zero syndrome is "corrected".
+__device__ __forceinline__ Dec4 h74_decode4(uint32_t x) {
+  const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3, x4 = x >> 4, x5 = x >> 5, x6 = x >> 6;
+  const uint32_t s0 = (x ^ x1 ^ x3 ^ x4) & M01;
+  const uint32_t s1 = (x ^ x2 ^ x3 ^ x5) & M01;
+  const uint32_t s2 = (x1 ^ x2 ^ x3 ^ x6) & M01;
+  const uint32_t f0 = s0 & s1 & ~s2, f1 = s0 & ~s1 & s2, f2 = ~s0 & s1 & s2, f3 = s0 & s1 & s2;
+  Dec4 r;
+  r.nib = (x & M0F) ^ (f0 | (f1 << 1) | (f2 << 2) | (f3 << 3));
+  r.nz = s0 | s1 | s2;
+  r.pe = 0;
+  return r;
+}
+
+// 0x01-per-byte flag word -> 0xFF-per-byte select mask
+__device__ __forceinline__ uint32_t spread8(uint32_t f01) { return (f01 << 8) - f01; }
+
+// Temporal interpolation of interpolation_triton.py:141-159 on nibble words: floor((l+r)*0.5+0.5) == (l+r+1)>>1 <= 15.
+__device__ __forceinline__ uint32_t interp4(uint32_t self, uint32_t left, uint32_t right, uint32_t dbl01) {
+  const uint32_t avg = ((left + right + M01) >> 1) & M0F;
+  const uint32_t m = spread8(dbl01);
+  return (self & ~m) | (avg & m);
+}
+
+// ------------------------------------------------------------------------------------------------ Golay(24,12)
+// Parity of data d (12 bit) = XOR of B rows of the set bits (linear code) = T_lo[d & 63] ^ T_hi[d >> 6];
+// B rows from config.py:329-347 (row i as a 12-bit mask, bit j = B[i][j]).  B is symmetric, so the same split table
+// gives the syndrome: s = parity(d) ^ (cw >> 12)  (golay_triton.py:161-189 with H = [B^T | I]).
+struct GolayTables {
+  uint16_t par_lo[64];
+  uint16_t par_hi[64];
+  int32_t syn[4096];  // config.py:403-457; -1 = uncorrectable
+};
+// Single translation unit (eccq_lib.cu), so the symbol is defined here; filled once per device by ensure_tables().
+__device__ GolayTables g_golay;
+
+__device__ __forceinline__ uint32_t golay_parity(const uint16_t* lo, const uint16_t* hi, uint32_t d) {
+  return (uint32_t)lo[d & 63u] ^ (uint32_t)hi[(d >> 6) & 63u];
+}
+__device__ __forceinline__ uint32_t golay_encode1(const uint16_t* lo, const uint16_t* hi, uint32_t d12) {
+  return d12 | (golay_parity(lo, hi, d12) << 12);
+}
+// returns corrected data (12 bit); cnt = bits corrected (0..3) or 4 when uncorrectable (data preserved,
+// golay_triton.py:262-286)
+__device__ __forceinline__ uint32_t golay_decode1(const uint16_t* lo, const uint16_t* hi, const int32_t* syn, uint32_t cw,
+                                                  uint32_t& cnt) {
+  const uint32_t d = cw & 0xFFFu;
+  const uint32_t s = golay_parity(lo, hi, d) ^ ((cw >> 12) & 0xFFFu);
+  const int32_t pat = syn[s];
+  const bool ok = pat >= 0;
+  cnt = ok ? (uint32_t)__popc(pat) : 4u;
+  return ok ? ((cw ^ (uint32_t)pat) & 0xFFFu) : d;
+}
+__device__ __forceinline__ void golay_load_parity(uint16_t* s_lo, uint16_t* s_hi) {
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    s_lo[i] = g_golay.par_lo[i];
+    s_hi[i] = g_golay.par_hi[i];
+  }
+}
+__device__ __forceinline__ void golay_load_syndrome(int32_t* s_syn) {
+  const int4* src = reinterpret_cast<const int4*>(g_golay.syn);
+  int4* dst = reinterpret_cast<int4*>(s_syn);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------ Philox-4x32-10
+// Exactly triton/language/random.py:philox_impl (uint32 branch): round constants 0xD2511F53 / 0xCD9E8D57,
+// key schedule 0x9E3779B9 / 0xBB67AE85.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hiA = __umulhi(0xD2511F53u, c.x), loA = 0xD2511F53u * c.x;
+    const uint32_t hiB = __umulhi(0xCD9E8D57u, c.z), loB = 0xCD9E8D57u * c.z;
+    c = make_uint4(hiB ^ c.y ^ k.x, loB, hiA ^ c.w ^ k.y, loA);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// triton uint_to_uniform_float: int32 view, x<0 -> -x-1, * 4.6566127342e-10f
+__device__ __forceinline__ float triton_uniform(uint32_t r) {
+  int32_t x = (int32_t)r;
+  x = x < 0 ? ~x : x;
+  return __int2float_rn(x) * 4.6566127342e-10f;
+}
+// tl.rand(seed.to(int32), off.to(int32)): int32 seed sign-extended to 64 bit -> (k0 = lo, k1 = hi); counter (off,0,0,0)
+__device__ __forceinline__ uint4 triton_philox(uint32_t key32, uint32_t off) {
+  return philox4x32_10(make_uint4(off, 0u, 0u, 0u), make_uint2(key32, (key32 >> 31) ? 0xFFFFFFFFu : 0u));
+}
+// Flip mask the reference's per-bit kernels produce for element `off` of an N-element launch
+// (fault_injection_triton.py:247-334): key = int32(seed*(N*n_bits) + off*n_bits + bit).
+__device__ __forceinline__ uint32_t ref_flip_mask(uint32_t seed_lo, uint32_t n, uint32_t off, int n_bits, float ber) {
+  const uint32_t base = seed_lo * (n * (uint32_t)n_bits) + off * (uint32_t)n_bits;
+  uint32_t m = 0;
+  for (int b = 0; b < n_bits; ++b) {
+    const uint4 r = triton_philox(base + (uint32_t)b, off);
+    m |= (triton_uniform(r.x) < ber ? 1u : 0u) << b;
+  }
+  return m;
+}
+// rand4x variant (fault_injection_triton.py:82-215): key = int32(seed*N + off + g*N), word j of call g -> bit 4g+j.
+__device__ __forceinline__ uint32_t ref_flip_mask_vec(uint32_t seed_lo, uint32_t n, uint32_t off, int n_bits, float ber) {
+  const uint32_t base = seed_lo * n + off;
+  uint32_t m = 0;
+  for (int g = 0; 4 * g < n_bits; ++g) {
+    const uint4 r = triton_philox(base + (uint32_t)g * n, off);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * g + j < n_bits) m |= (triton_uniform(w[j]) < ber ? 1u : 0u) << (4 * g + j);
+  }
+  return m;
+}
+
+// Own stream: i.i.d. Bernoulli(p) over `npos` candidate bit positions of one chunk by geometric gap sampling.
+// One Philox call = 4 gaps; expected calls per chunk = ceil((1 + npos*p)/4).  `hit(pos)` is invoked per flip.
+struct FastInject {
+  float inv_lg2_q;  // 1 / log2(1-p)  (negative); 0 => p >= 1 (flip everything)
+  uint32_t seed_lo, seed_hi;
+};
+template <class Hit>
+__device__ __forceinline__ void fast_flip_positions(const FastInject& fi, uint64_t chunk, int npos, Hit hit) {
+  if (fi.inv_lg2_q == 0.0f) {
+    for (int p = 0; p < npos; ++p) hit(p);
+    return;
+  }
+  float pos = -1.0f;
+  uint32_t call = 0;
+  for (;;) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)chunk, (uint32_t)(chunk >> 32), call++, 0x45434351u),
+                                  make_uint2(fi.seed_lo, fi.seed_hi));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float u = (float)((w[j] >> 8) + 1u) * 5.9604644775390625e-8f;  // (0,1], 24 bit
+      pos += floorf(__log2f(u) * fi.inv_lg2_q) + 1.0f;
+      if (!(pos < (float)npos)) return;
+      hit((int)pos);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ float <-> INT4
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+  static __device__ __forceinline__ float from(float v) { return v; }
+  static __device__ __forceinline__ float to(float v) { return v; }
+};
+template <> struct Cvt<__half> {
+  static __device__ __forceinline__ float from(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half to(float v) { return __float2half_rn(v); }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  static __device__ __forceinline__ float from(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 to(float v) { return __float2bfloat16_rn(v); }
+};
+
+// scale of paged_cache_ecc.py:328-334 (zero_guard 0) or quantization_backends.py:253-257 (zero_guard 1)
+__device__ __forceinline__ float make_scale(float amax, int zero_guard) {
+  if (zero_guard) return __fdiv_rn(fmaxf(amax, 1e-8f), 7.0f);
+  const float s = __fdiv_rn(amax, 7.0f);
+  return s == 0.0f ? 1.0f : s;
+}
+// exact: clamp(rint(x / scale), -8, 7) + 8 with an IEEE divide (ecc_shim.py:575-580; torch.round = half-to-even)
+__device__ __forceinline__ uint32_t quant_exact(float x, float scale) {
+  float q = rintf(__fdiv_rn(x, scale));
+  q = fminf(fmaxf(q, -8.0f), 7.0f);
+  return (uint32_t)((int)q + 8) & 0xFu;
+}
+// Fast path: t = x * (1/scale) differs from the IEEE quotient by a few ulp, which can only change the rounded
+// integer when the quotient sits within ~1e-5 of a tie; those (rare) elements are redone with quant_exact.
+// Magic-constant rounding: (t + 1.5*2^23) rounds to nearest-even integer, result in the low mantissa bits.
+constexpr float kMagic = 12582912.0f;
+__device__ __forceinline__ uint32_t quant_fast(float x, float rscale, float scale, float& worst) {
+  float t = x * rscale;
+  t = fminf(fmaxf(t, -8.25f), 7.25f);
+  const float m = t + kMagic;
+  const float k = m - kMagic;
+  worst = fmaxf(worst, fabsf(t - k));
+  (void)scale;
+  return (__float_as_uint(m) + 8u);  // low 4 bits valid after the caller masks with 0xF (k in [-8,7])
+}
+constexpr float kTieMargin = 0.5f - 2e-5f;
+
+// nibble byte k (0..255) -> float(k) exactly via the 2^23 mantissa trick
+__device__ __forceinline__ float byte_to_float_m8(uint32_t word, int byte_idx) {
+  const uint32_t sel = 0x7440u | (uint32_t)byte_idx;  // {b, 0x00, 0x00, 0x4B} from (word, 0x4B000000)
+  const uint32_t bits = __byte_perm(word, 0x4B000000u, sel);
+  return __uint_as_float(bits) - 8388616.0f;  // (2^23 + n) - (2^23 + 8)
+}
+
+}  // namespace eccq

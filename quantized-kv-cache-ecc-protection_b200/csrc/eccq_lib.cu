@@ -1,0 +1,47 @@
+// eccq_lib.cu -- the single translation unit of libeccq_sm100a.so (unity build: the kernels share one __device__
+// table symbol and are compiled for sm_100a only; no relocatable device code, no other architectures).
+#include "eccq_internal.h"
+
+namespace eccq {
+
+static std::mutex g_mu;
+
+int ensure_tables() {
+  DeviceState& s = device_state();
+  if (s.tables) return ECCQ_OK;
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (s.tables) return ECCQ_OK;
+  const GolayTables& t = host_golay_tables();
+  // synchronous on purpose: happens once per device, before the first kernel that needs the tables
+  const cudaError_t e = cudaMemcpyToSymbol(g_golay, &t, sizeof(GolayTables), 0, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
+  s.tables = true;
+  return ECCQ_OK;
+}
+
+}  // namespace eccq
+
+#include "eccq_codecs.cu"
+#include "eccq_cache.cu"
+#include "eccq_attention.cu"
+
+extern "C" int eccq_abi_version(void) { return ECCQ_ABI_VERSION; }
+extern "C" const char* eccq_last_error(void) { return eccq::last_error_ref(); }
+
+extern "C" int eccq_device_info(int device, int* out_host) {
+  if (!out_host) return eccq::fail(ECCQ_EINVAL, "device_info: null output");
+  cudaDeviceProp p;
+  const cudaError_t e = cudaGetDeviceProperties(&p, device);
+  if (e != cudaSuccess) return eccq::fail(ECCQ_ECUDA, cudaGetErrorString(e));
+  out_host[0] = p.multiProcessorCount;
+  out_host[1] = p.major;
+  out_host[2] = p.minor;
+  out_host[3] = (int)(p.l2CacheSize >> 20);
+  return ECCQ_OK;
+}
+
+extern "C" int eccq_golay_syndrome_table(int32_t* table_host) {
+  if (!table_host) return eccq::fail(ECCQ_EINVAL, "golay_syndrome_table: null output");
+  std::memcpy(table_host, eccq::host_golay_tables().syn, sizeof(int32_t) * 4096);
+  return ECCQ_OK;
+}

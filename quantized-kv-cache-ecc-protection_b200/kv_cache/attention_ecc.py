@@ -1,0 +1,128 @@
+"""
+ECC-fused paged decode attention on the CUDA backend: ``paged_attention_ecc`` and
+``reference_attention_ecc`` with the reference's signatures (kv_cache/attention_ecc.py:620-635, :783-795).
+
+Differences from the reference, all deliberate and tested:
+  * GQA caches are indexed with kv_head = q_head // group (the Triton kernel derives strides from the query
+    head count and is only correct for MHA);
+  * an empty context yields zeros (the Triton kernel returns -8.0, Q14);
+  * hamming74 / golay / hamming84+interpolation also run fused (the reference falls back to Python loops);
+  * the launch is split over the context (FlashDecoding) and never recompiles for a new max_blocks.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import _lib
+from .._lib import check, device_of, load, ptr, require_cuda, stream_of
+
+_workspaces: dict = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def _head_dim(k_cache, block_size, codec, query):
+    if codec == "golay":
+        return query.shape[-1]
+    return k_cache.shape[-1] // block_size
+
+
+def paged_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_scales, layer_idx, block_size, sm_scale=None,
+                        codec="hamming84", syndrome_table=None, use_tiled=False, block_m=4, v_scales=None, *,
+                        use_interpolation=False, counters=None):
+    """query [B, Hq, D] -> [B, Hq, D] in query.dtype.  `syndrome_table`, `use_tiled`, `block_m` are accepted for
+    signature compatibility and ignored (the tables live in the library; there is one kernel).  `counters`
+    (device int64[8]) receives corrected/detected counts when given."""
+    assert query.is_cuda, "Query must be on CUDA"
+    if codec not in ("hamming84", "hamming74", "golay", "int4"):
+        raise ValueError(f"Unknown codec: {codec}")
+    want = torch.int32 if codec == "golay" else torch.uint8
+    assert k_cache.dtype == want, f"{codec} K cache must be {want}"
+    assert v_cache.dtype == want, f"{codec} V cache must be {want}"
+    v_use_k = v_scales is None
+    if v_scales is None:
+        v_scales = k_scales
+    B, Hq, D = query.shape
+    qd = query if query.dtype in (torch.float32, torch.float16, torch.bfloat16) else query.float()
+    qd = qd.contiguous()
+    head_dim = _head_dim(k_cache, block_size, codec, query)
+    if head_dim != D:
+        raise ValueError(f"query head_dim {D} does not match the cache ({head_dim})")
+    if sm_scale is None:
+        sm_scale = 1.0 / math.sqrt(D)
+    bt = block_table.to(torch.int32).contiguous()
+    cl = context_lens.to(torch.int32).contiguous()
+    max_blocks = bt.shape[1]
+    desc = _lib.cache_desc(k_cache, v_cache, k_scales, v_scales, D, block_size, codec)
+    out = torch.empty_like(qd)
+    with device_of(qd):
+        lib = load()
+        nbytes = lib.eccq_attention_workspace_bytes(B, Hq, D, max_blocks * block_size)
+        ws = _workspace(qd.device, nbytes)
+        check(lib.eccq_paged_decode_attention(desc, ptr(qd), ptr(out), _lib.dtype_code(qd.dtype), ptr(bt), max_blocks, ptr(cl), B, Hq,
+                                              int(layer_idx), float(sm_scale), int(bool(use_interpolation)), int(v_use_k),
+                                              int(counters is not None), ptr(ws), ws.numel(), ptr(counters), stream_of(qd)),
+              "paged_attention_ecc")
+    return out if out.dtype == query.dtype else out.to(query.dtype)
+
+
+def read_cache(k_cache, v_cache, k_scales, v_scales, block_table, context_lens, layer_idx, block_size, head_dim, codec,
+               use_interpolation=False, out_dtype=torch.float32, counters=None, return_nibbles=False):
+    """Fused gather + decode + [interpolate] + dequantise of whole contexts: returns K, V
+    [nseq, max_ctx, Hkv, D] (tokens past context_len are zero).  The read half of ECCBackend.attend."""
+    require_cuda(k_cache)
+    bt = block_table.to(torch.int32).contiguous()
+    if bt.dim() == 1:
+        bt = bt.unsqueeze(0)
+    cl = context_lens.to(torch.int32).contiguous()
+    nseq, max_blocks = bt.shape
+    T = int(cl.max().item()) if cl.numel() else 0
+    H = k_cache.shape[2]
+    dev = k_cache.device
+    k_out = torch.zeros(nseq, T, H, head_dim, dtype=out_dtype, device=dev)
+    v_out = torch.zeros_like(k_out)
+    nk = nv = None
+    if return_nibbles:
+        nk = torch.zeros(nseq, T, H, head_dim, dtype=torch.uint8, device=dev)
+        nv = torch.zeros_like(nk)
+    if T > 0:
+        desc = _lib.cache_desc(k_cache, v_cache, k_scales, v_scales, head_dim, block_size, codec)
+        with device_of(k_cache):
+            check(load().eccq_cache_read(desc, ptr(bt), max_blocks, ptr(cl), nseq, T, int(layer_idx), int(bool(use_interpolation)),
+                                         _lib.dtype_code(out_dtype), ptr(k_out), ptr(v_out), ptr(nk), ptr(nv), ptr(counters),
+                                         stream_of(k_cache)), "cache_read")
+    if return_nibbles:
+        return k_out, v_out, nk, nv
+    return k_out, v_out
+
+
+def reference_attention_ecc(query, k_cache, v_cache, block_table, context_lens, scales, layer_idx, block_size, head_dim,
+                            sm_scale=None, codec="hamming84"):
+    """attention_ecc.py:783-909 (one `scales` tensor for K and V, Q15; fp32 output): decode the whole context with
+    the fused read kernel, then a plain fp32 softmax(QK^T)V in torch.  A second, independent route to the
+    same numbers as `paged_attention_ecc`, used by the tests."""
+    assert query.is_cuda, "Query must be on CUDA"
+    B, Hq, _ = query.shape
+    if sm_scale is None:
+        sm_scale = 1.0 / math.sqrt(head_dim)
+    k, v = read_cache(k_cache, v_cache, scales, scales, block_table, context_lens, layer_idx, block_size, head_dim, codec)
+    Hkv = k.shape[2]
+    out = torch.zeros(B, Hq, head_dim, device=query.device)
+    lens = context_lens.tolist()
+    for b in range(B):
+        c = int(lens[b])
+        if c <= 0:
+            continue
+        kb = k[b, :c].repeat_interleave(Hq // Hkv, dim=1).permute(1, 0, 2)
+        vb = v[b, :c].repeat_interleave(Hq // Hkv, dim=1).permute(1, 0, 2)
+        w = torch.softmax(torch.einsum("hd,hcd->hc", query[b].float(), kb) * sm_scale, dim=-1)
+        out[b] = torch.einsum("hc,hcd->hd", w, vb)
+    return out

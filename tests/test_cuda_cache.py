@@ -1,0 +1,194 @@
+"""Parity of the fused paged-cache write/read kernels and of ECCBackend.write/attend on the CUDA backend against
+(a) golden cache images produced by the REFERENCE's own ECCBackend (tests/golden/make_golden.py, Philox stream
+included) and (b) the CPU oracle on larger seeded cases."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MODES = (("hamming74", False), ("hamming84", False), ("hamming84", True), ("golay", False))
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _backend(codec, interp, ber, dims, injector="philox_ref", append=False):
+    from eccq_b200.kv_cache import ECCBackend, ECCShimConfig, SimpleBlockManager
+    B, S, Hq, Hkv, D, L, bs, nblk = dims
+    cfg = ECCShimConfig(codec=codec, ber=ber, block_size=bs, num_blocks=nblk, inject_errors=ber > 0, seed=42,
+                        use_interpolation=interp, backend="cuda", injector=injector, append=append)
+    mgr = SimpleBlockManager(nblk, bs, L, Hkv, D, device="cuda", codec=codec)
+    return ECCBackend(mgr, cfg, Hq), mgr
+
+
+@pytest.mark.parametrize("codec,interp", MODES)
+@pytest.mark.parametrize("ber", [0.0, 0.05])
+def test_backend_matches_reference_shim(golden, codec, interp, ber):
+    """Cache bytes, scales, attention outputs and counters equal the reference's ECCBackend on the same inputs,
+    including the fault-injection stream (bit-exact)."""
+    g = golden("shim_vectors")
+    dims = tuple(int(v) for v in g["dims"])
+    B, S, Hq, Hkv, D, L, bs, nblk = dims
+    tag = f"{codec}{'_interp' if interp else ''}_ber{ber}"
+    be, mgr = _backend(codec, interp, ber, dims)
+    be.write(dev(g["k"]), dev(g["v"]), layer_idx=1, seq_id=0)
+    assert np.array_equal(mgr.block_table[0].cpu().numpy(), g[tag + "_block_table"])
+    assert np.array_equal(mgr.k_cache.cpu().numpy(), g[tag + "_k_cache"]), tag
+    assert np.array_equal(mgr.v_cache.cpu().numpy(), g[tag + "_v_cache"]), tag
+    assert np.array_equal(mgr.k_scales.cpu().numpy().view(np.int32), g[tag + "_k_scales"].view(np.int32))
+    assert np.array_equal(mgr.v_scales.cpu().numpy().view(np.int32), g[tag + "_v_scales"].view(np.int32))
+    st = g[tag + "_stats"]
+    assert be._injection_count == int(st[0]) and be._total_values == int(st[5])
+    out = be.attend(dev(g["q_prefill"]), layer_idx=1, seq_id=0)
+    assert (be._errors_corrected, be._errors_detected) == (int(st[1]), int(st[2])), tag
+    assert np.abs(out.cpu().numpy() - g[tag + "_out_prefill"]).max() < 2e-5
+    # decode step (q_len == 1) through the fused attention kernel; the reference's GQA fast path is broken (Q13),
+    # so compare GQA against the reference's Python path numbers where it took that path, and MHA for hamming84
+    fast = codec == "hamming84" and not interp
+    out = be.attend(dev(g["q_decode"]), layer_idx=1, seq_id=0)
+    if not fast:
+        assert np.abs(out.cpu().numpy() - g[tag + "_out_decode"]).max() < 2e-5, tag
+    assert (be._errors_corrected, be._errors_detected) == (int(st[3]), int(st[4])), tag
+    from eccq_b200.kv_cache import ECCBackend
+    be_mha = ECCBackend(mgr, be.config, Hkv)
+    out = be_mha.attend(dev(g["q_decode"][:, :Hkv]), layer_idx=1, seq_id=0)
+    assert np.abs(out.cpu().numpy() - g[tag + "_out_decode_mha"]).max() < 2e-5, tag
+
+
+def _random_case(oracle, codec, D, bs, H, S, L, dtype, seed, ber, ragged_table=True):
+    rng = np.random.default_rng(seed)
+    nblk = -(-S // bs) + 3
+    k = rng.standard_normal((1, S, H * D)).astype(np.float32) * rng.random((1, S, 1)).astype(np.float32) * 3
+    v = rng.standard_normal((1, S, H * D)).astype(np.float32)
+    k[0, 1] = 0
+    kt, vt = torch.from_numpy(k).to(dtype), torch.from_numpy(v).to(dtype)
+    return nblk, kt, vt, kt.float().numpy(), vt.float().numpy()
+
+
+@pytest.mark.parametrize("codec", ["hamming84", "hamming74", "golay", "int4"])
+@pytest.mark.parametrize("D,bs", [(128, 16), (64, 16), (64, 8), (32, 4), (40, 16), (10, 4)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_write_read_vs_oracle_with_external_mask(oracle, codec, D, bs, dtype):
+    """Fused write (mask injection) and fused read (+interpolation) against the oracle: codewords, scales, corrected
+    nibbles, dequantised values and counters.  Covers the vectorised fast paths (D=128/64) and the generic kernels."""
+    H, S, L, layer = 3, 77, 2, 1
+    nblk, kt, vt, kn, vn = _random_case(oracle, codec, D, bs, H, S, L, dtype, seed=D * 131 + bs, ber=0.03)
+    from eccq_b200.kv_cache import ECCBackend, ECCShimConfig, SimpleBlockManager, read_cache
+    cfg = ECCShimConfig(codec=codec, block_size=bs, num_blocks=nblk, use_interpolation=codec == "hamming84")
+    mgr = SimpleBlockManager(nblk, bs, L, H, D, device="cuda", codec=codec)
+    # scramble the free list so pages are not contiguous
+    rng = np.random.default_rng(7)
+    mgr.free_blocks = [int(b) for b in rng.permutation(nblk)]
+    be = ECCBackend(mgr, cfg, H)
+    cw = oracle.golay_cw_per_row(D) if codec == "golay" else D
+    nbits = oracle.CODEC_BITS[codec]
+    flips = rng.random((1, S, H, cw, nbits)) < 0.03
+    mask = (flips * (1 << np.arange(nbits))).sum(-1)
+    mask_np = mask.astype(np.int32 if codec == "golay" else np.uint8)
+    vmask_np = np.roll(mask_np, 5, axis=1)
+    be.set_flip_masks(dev(mask_np), dev(vmask_np))
+    be.write(kt.cuda(), vt.cuda(), layer_idx=layer, seq_id=0)
+    oc = oracle.PagedCache(nblk, bs, L, H, D, codec)
+    bt = mgr.block_table[0].cpu().numpy()
+    oracle.cache_write(oc, kn, vn, layer, bt, k_mask=mask_np, v_mask=vmask_np)
+    assert np.array_equal(mgr.k_cache.cpu().numpy(), oc.k_cache)
+    assert np.array_equal(mgr.v_cache.cpu().numpy(), oc.v_cache)
+    assert np.array_equal(mgr.k_scales.cpu().numpy(), oc.k_scales) and np.array_equal(mgr.v_scales.cpu().numpy(), oc.v_scales)
+    assert be._bits_flipped == int(flips.sum()) * 2
+    for interp in ((False, True) if codec == "hamming84" else (False,)):
+        ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+        cl = torch.tensor([S], dtype=torch.int32, device="cuda")
+        kf, vf, nk, nv = read_cache(mgr.k_cache, mgr.v_cache, mgr.k_scales, mgr.v_scales, mgr.block_table[:1], cl, layer, bs, D,
+                                    codec, use_interpolation=interp, out_dtype=torch.float32, counters=ctr, return_nibbles=True)
+        okf, ovf, corr, det = oracle.cache_read(oc, layer, bt, S, use_interpolation=interp)
+        assert np.array_equal(kf[0].cpu().numpy(), okf) and np.array_equal(vf[0].cpu().numpy(), ovf), (codec, interp)
+        assert (int(ctr[0]), int(ctr[1])) == (corr, det)
+        # corrected (+interpolated) INT4 codes
+        kc, vc, ks, vs = oracle.cache_gather(oc, layer, bt, S)
+        kd, _, _ = oracle.decode_rows(kc, codec, D, interp)
+        assert np.array_equal(nk[0].cpu().numpy(), kd)
+        # half-precision outputs: one rounding of the fp32 product, like the reference's .to(q.dtype)
+        for odt in (torch.float16, torch.bfloat16):
+            kh, vh = read_cache(mgr.k_cache, mgr.v_cache, mgr.k_scales, mgr.v_scales, mgr.block_table[:1], cl, layer, bs, D, codec,
+                                use_interpolation=interp, out_dtype=odt)
+            assert torch.equal(kh[0].cpu(), torch.from_numpy(okf).to(odt)) and torch.equal(vh[0].cpu(), torch.from_numpy(ovf).to(odt))
+
+
+def test_ragged_contexts_and_partial_blocks(oracle):
+    """Several sequences with different context lengths (append mode), context ends inside a block, interpolation
+    neighbours across page boundaries."""
+    from eccq_b200.kv_cache import ECCBackend, ECCShimConfig, SimpleBlockManager, read_cache
+    D, bs, H, L = 128, 16, 2, 1
+    lens = [1, 16, 17, 47, 64]
+    nblk = sum(-(-n // bs) for n in lens) + 2
+    cfg = ECCShimConfig(codec="hamming84", ber=0.04, inject_errors=True, block_size=bs, num_blocks=nblk, use_interpolation=True,
+                        append=True)
+    mgr = SimpleBlockManager(nblk, bs, L, H, D, device="cuda", codec="hamming84")
+    mgr.free_blocks = [int(b) for b in np.random.default_rng(3).permutation(nblk)]
+    be = ECCBackend(mgr, cfg, H)
+    oc = oracle.PagedCache(nblk, bs, L, H, D, "hamming84")
+    rng = np.random.default_rng(11)
+    cnt = 0
+    for i, n in enumerate(lens):   # one sequence per write call (append mode maps batch row b -> seq_id + b)
+        k = rng.standard_normal((1, n, H * D)).astype(np.float32)
+        v = rng.standard_normal((1, n, H * D)).astype(np.float32)
+        be.write(dev(k).half(), dev(v).half(), 0, seq_id=i)
+        kh, vh = torch.from_numpy(k).half().float().numpy(), torch.from_numpy(v).half().float().numpy()
+        cnt = oracle.cache_write(oc, kh, vh, 0, mgr.block_table[i].cpu().numpy(), ber=0.04, seed=42, injection_count=cnt)
+    assert np.array_equal(mgr.k_cache.cpu().numpy(), oc.k_cache) and np.array_equal(mgr.v_cache.cpu().numpy(), oc.v_cache)
+    cl = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+    kf, vf = read_cache(mgr.k_cache, mgr.v_cache, mgr.k_scales, mgr.v_scales, mgr.block_table[:len(lens)], cl, 0, bs, D, "hamming84",
+                        use_interpolation=True, counters=ctr)
+    tc = td = 0
+    for i, n in enumerate(lens):
+        okf, ovf, c, d = oracle.cache_read(oc, 0, mgr.block_table[i].cpu().numpy(), n, use_interpolation=True)
+        assert np.array_equal(kf[i, :n].cpu().numpy(), okf) and np.array_equal(vf[i, :n].cpu().numpy(), ovf), i
+        assert not kf[i, n:].any()
+        tc, td = tc + c, td + d
+    assert (int(ctr[0]), int(ctr[1])) == (tc, td) and td > 0
+
+
+def test_write_fast_injector_statistics():
+    """philox_fast in the fused write: flips ~ Binomial(bits, ber), decode counters follow SURVEY 2.4."""
+    from eccq_b200.kv_cache import ECCBackend, ECCShimConfig, SimpleBlockManager, read_cache
+    D, bs, H, L, S = 128, 16, 8, 1, 4096
+    nblk = S // bs
+    for codec, nbits, p_corr in (("hamming84", 8, 6.529118e-2), ("hamming74", 7, 6.792786e-2), ("golay", 24, 2.396447e-1)):
+        cfg = ECCShimConfig(codec=codec, ber=1e-2, inject_errors=True, block_size=bs, num_blocks=nblk, injector="philox_fast")
+        mgr = SimpleBlockManager(nblk, bs, L, H, D, device="cuda", codec=codec)
+        be = ECCBackend(mgr, cfg, H)
+        x = torch.randn(1, S, H * D, device="cuda", dtype=torch.float16)
+        be.write(x, x.flip(1), 0)
+        cw = (D + 2) // 3 if codec == "golay" else D
+        bits = 2 * S * H * cw * nbits
+        flips = be._bits_flipped
+        assert abs(flips - bits * 1e-2) < 5 * (bits * 1e-2) ** 0.5
+        cl = torch.tensor([S], dtype=torch.int32, device="cuda")
+        ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+        read_cache(mgr.k_cache, mgr.v_cache, mgr.k_scales, mgr.v_scales, mgr.block_table[:1], cl, 0, bs, D, codec, counters=ctr)
+        ncw = 2 * S * H * cw
+        exp = ncw * p_corr
+        assert abs(int(ctr[0]) - exp) < 6 * exp ** 0.5, (codec, int(ctr[0]), exp)
+
+
+def test_block_manager_and_stats_api():
+    from eccq_b200.kv_cache import ECCShimConfig, SimpleBlockManager
+    m = SimpleBlockManager(8, 4, 2, 2, 16, device="cuda", codec="golay")
+    assert m.k_cache.shape == (8, 2, 2, 4 * 6) and m.k_cache.dtype == torch.int32 and m.k_scales.shape == (8, 2, 2, 4)
+    row, n = m.allocate(0, 9)
+    assert n == 9 and row[:3].tolist() == [0, 1, 2] and row[3].item() == -1 and len(m.free_blocks) == 5
+    m.allocate(0, 13)
+    assert m.get_block_table(0)[:4].tolist() == [0, 1, 2, 3] and m.get_context_len(0) == 13
+    with pytest.raises(RuntimeError, match="Out of blocks"):
+        m.allocate(1, 100)
+    m.reset()
+    assert len(m.free_blocks) == 8 and (m.block_table == -1).all() and m.get_context_len(0) == 0
+    with pytest.raises(ValueError):
+        ECCShimConfig(codec="adaptive")
+    with pytest.raises(ValueError):
+        ECCShimConfig(backend="triton")
+    with pytest.raises(NotImplementedError):
+        SimpleBlockManager(8, 4, 2, 2, 16, device="cuda", codec="fp16")
