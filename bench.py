@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the ECC-protected INT4 KV-cache hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W     (one rank per GPU)
+
+Workload (BASELINE.json configs[2], "C3"): LLaMA-3.1-8B KV shape, one layer, batch 16 x seq 8192 x 8 KV heads x 128,
+fp16 activations, Hamming(8,4) + temporal interpolation, BER 1e-2.  One STEP = one pass of the hot path over that
+batch: fused cache write (INT4 quantise + encode + Philox fault injection + paged scatter, K and V) followed by
+fused cache read (gather + syndrome decode + correct + SECDED flag + interpolate + dequantise to fp16, K and V).
+The read consumes the cache image written one step earlier (two images ping-pong), so every byte it touches has been
+evicted from the 126 MB L2 by >1 GB of intervening traffic; the fp16 inputs (537 MB) are far larger than L2.
+
+Prints ONE JSON line (rank 0): whole-job algorithmic GB/s (`value`, inputs resident in HBM), `e2e` through the public
+Python API from pinned host buffers, the live `roofline` of the dominant kernel against MEASURED_PEAKS.json, the same
+work on the host cores (`cpu_baseline`, the oracle's C port), clocks sampled during the timed region, launch count.
+`--impl reference` times the CPU port alone (the reference has no CPU codec of its own).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+# ---- workload constants (C3, per GPU) ------------------------------------------------------------------------------
+B, S, HKV, HQ, D, BS = 16, 8192, 8, 32, 128, 16
+CODEC, BER, SEED = "hamming84", 1e-2, 42
+VALUES_PER_TENSOR = B * S * HKV * D                       # 134 217 728
+BYTES_WRITE = 2 * VALUES_PER_TENSOR * (3.0 + 4.0 / D)     # K and V: 2 B in + 1 B out + 4/D B scale per value
+BYTES_READ = 2 * VALUES_PER_TENSOR * (3.0 + 4.0 / D)      # K and V: 1 B + 4/D B in, 2 B out per value
+BYTES_STEP = BYTES_WRITE + BYTES_READ
+METRIC, UNIT = "ecc_kv_cache_codec_throughput", "GB/s"
+
+
+def hbm_peak():
+    try:
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU leg: the oracle's C port on the host cores -----------------------------------------------------------------
+def cpu_leg(steps: int, warmup: int, sample_seqs: int = 4, min_seconds: float = 0.0):
+    """One step = the same pipeline (quantise+encode -> flip mask -> decode+interpolate+dequantise, K and V) on a bounded
+    sample of the C3 batch: `sample_seqs` of the 16 sequences."""
+    from oracle import c_port
+    rng = np.random.default_rng(SEED)
+    rows = sample_seqs * S
+    k = rng.standard_normal((rows, HKV, D), dtype=np.float32)
+    v = rng.standard_normal((rows, HKV, D), dtype=np.float32)
+    mask = ((rng.random((rows, HKV, D, 1)) < 8 * BER) * (1 << rng.integers(0, 8, (rows, HKV, D, 1)))).astype(np.uint8)[..., 0]
+    out = np.empty((rows, HKV, D), dtype=np.float32)
+    noisy = np.empty((rows, HKV, D), dtype=np.uint8)
+    values = 2 * rows * HKV * D
+
+    def step():
+        for x in (k, v):
+            cw, sc = c_port.quantize_encode_h84(x)
+            c_port.xor_mask(cw, mask, noisy)
+            c_port.decode_interp_dequant_h84(noisy, sc, True, out)
+
+    for _ in range(max(1, warmup)):
+        step()
+    times = []
+    t_begin = time.perf_counter()
+    while len(times) < max(1, steps) or time.perf_counter() - t_begin < min_seconds:
+        t = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t)
+    med = statistics.median(times)
+    gbs = values * (6.0 + 8.0 / D) / med / 1e9
+    return {"value": gbs, "unit": UNIT, "cores": c_port.num_threads(), "kind": "port",
+            "sample": f"{sample_seqs}/{B} sequences of the C3 batch ({values} INT4 values per step, fp32 in/out, external flip mask), "
+                      f"median of {len(times)} steps, {med * 1e3:.1f} ms/step, oracle/eccq_oracle.c with OpenMP",
+            "ms_per_step": med * 1e3, "mvalues_per_s": values / med / 1e6}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_leg(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C3 LLaMA-3.1-8B KV codec path, Hamming(8,4)+interp, BER 1e-2 (bounded CPU sample)",
+                       "note": "the reference ships no CPU codec (all wrappers assert CUDA); this is the oracle's C port"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks -----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._thr = [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        while not self._stop.is_set():
+            self.sample()
+            time.sleep(0.002)
+
+    def sample(self):
+        if self.nv is None:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def __enter__(self):
+        self._stop.clear()
+        self._thr = threading.Thread(target=self._poll, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thr.join()
+
+    def report(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- GPU leg ----------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from eccq_b200 import _lib
+    from eccq_b200.distributed import all_reduce_counters, init_from_env, max_over_ranks
+    from eccq_b200.kv_cache import ECCBackend, ECCShimConfig, SimpleBlockManager, paged_attention_ecc, read_cache
+
+    rank, world, local = init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    # weak scaling: every rank owns a full C3 batch (its own sequences and block pool); strong: the 16 sequences are split
+    b_local = B if args.scaling == "weak" else max(1, B // world)
+    nblk_seq = S // BS
+    nblk = b_local * nblk_seq
+    gen = torch.Generator(device=dev).manual_seed(SEED + rank)
+    k = torch.randn(b_local, S, HKV * D, device=dev, dtype=torch.float16, generator=gen)
+    v = torch.randn(b_local, S, HKV * D, device=dev, dtype=torch.float16, generator=gen)
+    cfg = ECCShimConfig(codec=CODEC, ber=BER, inject_errors=True, seed=SEED, block_size=BS, num_blocks=nblk, use_interpolation=True,
+                        backend="cuda", injector="philox_fast", append=True)
+    images = []
+    for _ in range(2):  # two cache images ping-pong (see module docstring)
+        m = SimpleBlockManager(nblk, BS, 1, HKV, D, device=dev, codec=CODEC)
+        m.max_seqs = b_local
+        perm = torch.randperm(nblk, generator=torch.Generator().manual_seed(7 + rank)).to(torch.int32)
+        m.block_table = perm.view(b_local, nblk_seq).to(dev)           # random page placement per sequence
+        images.append(m)
+    counters = _lib.new_counters(dev)
+    cl = torch.full((b_local,), S, dtype=torch.int32, device=dev)
+    k_out = torch.empty(b_local, S, HKV, D, device=dev, dtype=torch.float16)
+    v_out = torch.empty_like(k_out)
+    stream = torch.cuda.current_stream(dev)
+    sp = _lib.c_void_p(stream.cuda_stream)
+    descs = [m.desc() for m in images]
+    P = _lib.ptr
+
+    def k_write(i):
+        m = images[i]
+        _lib.check(lib.eccq_cache_write(descs[i], P(k), P(v), _lib.ECCQ_F16, P(m.block_table), nblk_seq, None, b_local, S, 0,
+                                        _lib.INJECT_PHILOX_FAST, None, None, BER, SEED, i, P(counters), sp), "cache_write")
+
+    def k_read(i):
+        m = images[i]
+        _lib.check(lib.eccq_cache_read(descs[i], P(m.block_table), nblk_seq, P(cl), b_local, S, 0, 1, _lib.ECCQ_F16, P(k_out), P(v_out),
+                                       None, None, P(counters), sp), "cache_read")
+
+    def step(i):
+        k_write(i & 1)
+        k_read((i + 1) & 1)
+
+    k_write(1)  # the image the first read consumes
+    for i in range(max(3, args.warmup)):
+        step(i)
+    t_end = time.perf_counter() + 0.3  # let the SM/memory clocks ramp up before timing (idle clocks are 120 MHz)
+    i = 0
+    while time.perf_counter() < t_end:
+        step(i)
+        i += 1
+        if i % 16 == 0:
+            torch.cuda.synchronize(dev)
+    torch.cuda.synchronize(dev)
+
+    # ---------------- timed region: exactly K steps, device-timed, per-kernel events on the launching stream
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local)
+    with sampler:
+        for i in range(K):
+            ev[i][0].record(stream)
+            k_write(i & 1)
+            ev[i][1].record(stream)
+            k_read((i + 1) & 1)
+            ev[i][2].record(stream)
+        sampler.sample()
+        torch.cuda.synchronize(dev)
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    w_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+    r_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
+    total_ms = max_over_ranks(total_ms, dev)
+    if world > 1:
+        torch.distributed.barrier()
+    scale = b_local / B
+    value = world * K * BYTES_STEP * scale / (total_ms * 1e-3) / 1e9
+    peak, peak_src = hbm_peak()
+    kern = {"cache_write_kernel": {"ms": w_ms, "gbs": BYTES_WRITE * scale / (w_ms * 1e-3) / 1e9},
+            "cache_read_kernel": {"ms": r_ms, "gbs": BYTES_READ * scale / (r_ms * 1e-3) / 1e9}}
+    dom = max(kern, key=lambda n: kern[n]["ms"])
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"   # dram bytes per launch from the committed ncu --set full capture
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": (BYTES_WRITE if dom == "cache_write_kernel" else BYTES_READ) * scale,
+                "frac_of_nominal_8TBps": kern[dom]["gbs"] / 8000.0}
+
+    # ---------------- statistics: the only collective of the path (NCCL all-reduce of the counter vector)
+    stats = all_reduce_counters(counters).tolist()
+
+    # ---------------- e2e: public Python API, pinned host buffers, H2D of K/V and D2H of the counters inside the region
+    be = ECCBackend(images[0], cfg, HQ)
+    kh = torch.empty(k.shape, dtype=k.dtype, pin_memory=True).copy_(k)
+    vh = torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v)
+    ctr_host = torch.empty(_lib.NCOUNTERS, dtype=torch.int64, pin_memory=True)
+    n_e2e = max(2, min(K, 10))
+
+    def e2e_step():
+        images[0].seq_to_len.clear()   # every step writes positions [0, S) of its 16 sequences again
+        kd = kh.to(dev, non_blocking=True)
+        vd = vh.to(dev, non_blocking=True)
+        be.write(kd, vd, 0, seq_id=0)
+        read_cache(images[0].k_cache, images[0].v_cache, images[0].k_scales, images[0].v_scales, images[0].block_table, cl, 0, BS, D,
+                   CODEC, use_interpolation=True, out_dtype=torch.float16, counters=be._counters, max_context=S, out=(k_out, v_out))
+        ctr_host.copy_(be._counters, non_blocking=True)
+
+    # append-mode bookkeeping of the manager: the blocks are already mapped by the benchmark's own block table
+    images[0].seq_to_blocks = {b: images[0].block_table[b].tolist() for b in range(b_local)}
+    images[0].free_blocks = []
+    e2e_step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        torch.distributed.barrier()
+    e0.record(stream)
+    for _ in range(n_e2e):
+        e2e_step()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    e2e = {"value": world * n_e2e * BYTES_STEP * scale / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": int(2 * k.numel() * k.element_size()), "d2h_bytes_per_step": int(ctr_host.numel() * 8),
+           "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
+           "api": "ECCBackend.write + kv_cache.read_cache from pinned host fp16 K/V; result read back = counter vector"}
+
+    # ---------------- secondary metric: ECC-fused paged decode attention, C5 per-GPU shard (batch 8 x 32k context)
+    attn = None
+    if not args.no_attention:
+        try:
+            attn = bench_attention(torch, dev, lib, _lib, paged_attention_ecc, SimpleBlockManager, world)
+        except Exception as exc:  # never lose the headline line to the secondary metric
+            attn = {"error": repr(exc)}
+
+    if rank == 0:
+        cb = cpu_leg(3, 1, min_seconds=10.0) if not args.no_cpu else None   # ~10 s of host work
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8",
+                "data": "synthetic",
+                "config": {"workload": "C3: LLaMA-3.1-8B KV shape, 1 layer, fused cache write + fused cache read, Hamming(8,4)+interpolation",
+                           "per_gpu_batch": b_local, "seq_len": S, "kv_heads": HKV, "head_dim": D, "block_size": BS, "io_dtype": "fp16",
+                           "ber": BER, "injector": "philox_fast (on-device)", "sharding": f"batch, {world} rank(s), no data-path collective",
+                           "l2": "inputs 537 MB >> 126 MB L2; read consumes the cache image written one step earlier (ping-pong)",
+                           "algorithmic_bytes_per_step": BYTES_STEP * scale},
+                "roofline": roofline, "kernels": kern, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": 2 * K,
+                "clocks": sampler.report(),
+                "counters": {"corrected": stats[0], "detected": stats[1], "bits_flipped": stats[2], "interpolated": stats[5]},
+                "decode_attention": attn}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def bench_attention(torch, dev, lib, _lib, paged_attention_ecc, SimpleBlockManager, world):
+    """C5 shard: 8 sequences x 32 768 context, Hq 32 / Hkv 8 / D 128, Hamming(8,4) codewords consumed directly."""
+    Bq, ctx = 8, 32768
+    nblk_seq = ctx // BS
+    nblk = Bq * nblk_seq
+    m = SimpleBlockManager(nblk, BS, 1, HKV, D, device=dev, codec=CODEC)
+    m.block_table = torch.randperm(nblk, generator=torch.Generator().manual_seed(3)).to(torch.int32).view(Bq, nblk_seq).to(dev)
+    P = _lib.ptr
+    sp = _lib.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    chunk = 4096
+    for s0 in range(0, ctx, chunk):  # fill the cache with the fused write kernel, 4k tokens at a time
+        kk = torch.randn(Bq, chunk, HKV * D, device=dev, dtype=torch.float16)
+        start = torch.full((Bq,), s0, dtype=torch.int32, device=dev)
+        _lib.check(lib.eccq_cache_write(m.desc(), P(kk), P(kk.flip(1)), _lib.ECCQ_F16, P(m.block_table), nblk_seq, P(start), Bq, chunk, 0,
+                                        _lib.INJECT_PHILOX_FAST, None, None, 1e-3, 1, s0, None, sp), "cache_write")
+    q = torch.randn(Bq, HQ, D, device=dev, dtype=torch.float16)
+    cl = torch.full((Bq,), ctx, dtype=torch.int32, device=dev)
+
+    def run():
+        return paged_attention_ecc(q, m.k_cache, m.v_cache, m.block_table, cl, m.k_scales, 0, BS, v_scales=m.v_scales)
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize(dev)
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / n
+    nbytes = Bq * ctx * (2 * HKV * D + 2 * HKV * 4)
+    peak, _ = hbm_peak()
+    return {"workload": "C5 shard: batch 8 x 32768 ctx, Hq 32, Hkv 8, D 128, block 16, Hamming(8,4), q_len 1, one layer",
+            "ms_per_layer_call": ms, "context_tokens_per_s_per_gpu": Bq * ctx / (ms * 1e-3),
+            "context_tokens_per_s_all_gpus": world * Bq * ctx / (ms * 1e-3),
+            "generated_tokens_per_s_32_layers": world * Bq / (32 * ms * 1e-3), "gbs": nbytes / (ms * 1e-3) / 1e9,
+            "roofline_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "kernel": "attn_partial_kernel (v0, CUDA cores) + attn_merge_kernel"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-attention", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

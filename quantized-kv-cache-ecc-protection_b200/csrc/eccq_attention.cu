@@ -292,8 +292,9 @@ static int dispatch_attn(const CacheGeom& g, const AttnArgs& a, uint64_t* counte
   const int G = a.Hq / g.H;
   const int per_chunk = CODEC == ECCQ_CODEC_GOLAY ? 96 : 128;
   const int nch = (g.D + per_chunk - 1) / per_chunk;
-  if (nch > 2) return fail(ECCQ_EUNSUPPORTED, "paged_decode_attention: head_dim too large");
-#define ECCQ_ATTN_CASE(GPV)                                                                           \
+  if (nch > (CODEC == ECCQ_CODEC_GOLAY ? 3 : 2)) return fail(ECCQ_EUNSUPPORTED, "paged_decode_attention: head_dim too large (max 256)");
+#define ECCQ_ATTN_CASE(GPV)                                                                                        \
+  if (CODEC == ECCQ_CODEC_GOLAY && nch == 3) return launch_attn<TQ, CODEC, GPV, (CODEC == ECCQ_CODEC_GOLAY ? 3 : 2)>(g, a, counters, st); \
   return nch == 1 ? launch_attn<TQ, CODEC, GPV, 1>(g, a, counters, st) : launch_attn<TQ, CODEC, GPV, 2>(g, a, counters, st)
   if (G == 1) { ECCQ_ATTN_CASE(1); }
   if (G == 2) { ECCQ_ATTN_CASE(2); }

@@ -75,20 +75,32 @@ def paged_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_sc
 
 
 def read_cache(k_cache, v_cache, k_scales, v_scales, block_table, context_lens, layer_idx, block_size, head_dim, codec,
-               use_interpolation=False, out_dtype=torch.float32, counters=None, return_nibbles=False):
+               use_interpolation=False, out_dtype=torch.float32, counters=None, return_nibbles=False, max_context=None, out=None):
     """Fused gather + decode + [interpolate] + dequantise of whole contexts: returns K, V
-    [nseq, max_ctx, Hkv, D] (tokens past context_len are zero).  The read half of ECCBackend.attend."""
+    [nseq, max_ctx, Hkv, D] (tokens past context_len are zero).  The read half of ECCBackend.attend.
+
+    max_context: longest context if the caller knows it (saves the one host sync used to size the outputs).
+    out:         optional preallocated (k_out, v_out); tokens past a sequence's context are then left untouched."""
     require_cuda(k_cache)
     bt = block_table.to(torch.int32).contiguous()
     if bt.dim() == 1:
         bt = bt.unsqueeze(0)
     cl = context_lens.to(torch.int32).contiguous()
     nseq, max_blocks = bt.shape
-    T = int(cl.max().item()) if cl.numel() else 0
+    if max_context is None:
+        lens = cl.tolist()
+        T, ragged = (max(lens), min(lens) != max(lens)) if lens else (0, False)
+    else:
+        T, ragged = int(max_context), True
     H = k_cache.shape[2]
     dev = k_cache.device
-    k_out = torch.zeros(nseq, T, H, head_dim, dtype=out_dtype, device=dev)
-    v_out = torch.zeros_like(k_out)
+    if out is not None:
+        k_out, v_out = out
+        T = k_out.shape[1]
+    else:
+        alloc = torch.zeros if ragged else torch.empty
+        k_out = alloc(nseq, T, H, head_dim, dtype=out_dtype, device=dev)
+        v_out = alloc(nseq, T, H, head_dim, dtype=out_dtype, device=dev)
     nk = nv = None
     if return_nibbles:
         nk = torch.zeros(nseq, T, H, head_dim, dtype=torch.uint8, device=dev)
@@ -97,7 +109,7 @@ def read_cache(k_cache, v_cache, k_scales, v_scales, block_table, context_lens, 
         desc = _lib.cache_desc(k_cache, v_cache, k_scales, v_scales, head_dim, block_size, codec)
         with device_of(k_cache):
             check(load().eccq_cache_read(desc, ptr(bt), max_blocks, ptr(cl), nseq, T, int(layer_idx), int(bool(use_interpolation)),
-                                         _lib.dtype_code(out_dtype), ptr(k_out), ptr(v_out), ptr(nk), ptr(nv), ptr(counters),
+                                         _lib.dtype_code(k_out.dtype), ptr(k_out), ptr(v_out), ptr(nk), ptr(nv), ptr(counters),
                                          stream_of(k_cache)), "cache_read")
     if return_nibbles:
         return k_out, v_out, nk, nv
