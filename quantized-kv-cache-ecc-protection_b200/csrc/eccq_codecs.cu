@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(kThreads) hamming_encode_kernel(const uint8_t*
 }
 
 // ------------------------------------------------------------------------------------------------ Hamming decode
+// counts accumulate as byte-wide sums inside `ncorr`/`ndet` words (flushed with bytesum() before a byte can overflow)
 template <int CODEC, bool ZERO_DOUBLE>
 __device__ __forceinline__ void dec4(uint32_t x, uint32_t& nib, uint32_t& aux, uint32_t& ncorr, uint32_t& ndet) {
   if (CODEC == ECCQ_CODEC_H84) {
@@ -52,13 +53,13 @@ __device__ __forceinline__ void dec4(uint32_t x, uint32_t& nib, uint32_t& aux, u
     const uint32_t dbl = h84_double4(d);
     nib = ZERO_DOUBLE ? (d.nib & ~spread8(dbl)) : d.nib;
     aux = h84_etype4(d);
-    ncorr += __popc(h84_single4(d));
-    ndet += __popc(dbl);
+    ncorr += h84_single4(d);
+    ndet += dbl;
   } else {
     const Dec4 d = h74_decode4(x);
     nib = d.nib;
     aux = d.nz;
-    ncorr += __popc(d.nz);
+    ncorr += d.nz;
   }
 }
 
@@ -84,10 +85,13 @@ __global__ void __launch_bounds__(kThreads) hamming_decode_kernel(const uint8_t*
         const int64_t j = i + (int64_t)u * nthreads;
         if (j < n16) {
           uint4 o, a;
-          dec4<CODEC, ZERO_DOUBLE>(v[u].x, o.x, a.x, ncorr, ndet);
-          dec4<CODEC, ZERO_DOUBLE>(v[u].y, o.y, a.y, ncorr, ndet);
-          dec4<CODEC, ZERO_DOUBLE>(v[u].z, o.z, a.z, ncorr, ndet);
-          dec4<CODEC, ZERO_DOUBLE>(v[u].w, o.w, a.w, ncorr, ndet);
+          uint32_t ac = 0, ad = 0;
+          dec4<CODEC, ZERO_DOUBLE>(v[u].x, o.x, a.x, ac, ad);
+          dec4<CODEC, ZERO_DOUBLE>(v[u].y, o.y, a.y, ac, ad);
+          dec4<CODEC, ZERO_DOUBLE>(v[u].z, o.z, a.z, ac, ad);
+          dec4<CODEC, ZERO_DOUBLE>(v[u].w, o.w, a.w, ac, ad);
+          ncorr += bytesum(ac);
+          ndet += bytesum(ad);
           st_stream(nib_out + (j << 4), o);
           if (aux_out) st_stream(aux_out + (j << 4), a);
         }
@@ -96,8 +100,10 @@ __global__ void __launch_bounds__(kThreads) hamming_decode_kernel(const uint8_t*
     done = n16 << 4;
   }
   for (int64_t i = done + tid; i < n; i += nthreads) {
-    uint32_t o, a;
-    dec4<CODEC, ZERO_DOUBLE>(in[i], o, a, ncorr, ndet);
+    uint32_t o, a, ac = 0, ad = 0;
+    dec4<CODEC, ZERO_DOUBLE>(in[i], o, a, ac, ad);
+    ncorr += ac & 0xFFu;
+    ndet += ad & 0xFFu;
     nib_out[i] = (uint8_t)o;
     if (aux_out) aux_out[i] = (uint8_t)a;
   }

@@ -67,26 +67,30 @@ struct Dec4 {
   uint32_t pe;   // 0x01 per byte: overall-parity mismatch (Hamming(8,4) only)
 };
 
-// Syndrome bits of hamming84_triton.py:160-164; the LUT [-1,4,5,0,6,1,2,3] only touches a DATA bit for syndromes
-// 3,5,6,7 (bits 0,1,2,3), which is all the decoded nibble can see, so the correction is four AND terms.
+// Syndrome decode of hamming84_triton.py:116-209 on four codeword bytes at once.
+//   y = x ^ x>>4 folds the parity nibble onto the data nibble (y_i = c_i ^ c_{i+4}), z = x ^ x>>2 gives c0^c2 / c1^c3, so
+//   s0 = y0^(c1^c3), s1 = y1^(c0^c2)^(c1^c3), s2 = y2^(c1^c3), overall parity mismatch pe = y0^y1^y2^y3.
+//   The 8-entry syndrome table [-1,4,5,0,6,1,2,3] (config.py:131-161) only reaches a DATA bit for syndromes 3,5,6,7
+//   (bits 0..3); it is applied as a register-resident byte LUT through PRMT: the four 3-bit syndromes are packed into one
+//   selector and index the 8-byte table {0,0,0,1,0,2,4,8} (and {0,1,1,1,1,1,1,1} for "syndrome != 0").
+//   The 0/1 masks are widened with IMAD (FMA pipe) to keep the ALU pipe, the bottleneck of these kernels, lighter.
+__device__ __forceinline__ uint32_t hamming_syndrome_sel(uint32_t x, uint32_t& y) {
+  y = x ^ (x >> 4);
+  const uint32_t z = x ^ (x >> 2);
+  const uint32_t a = ((z >> 1) & M01) * 7u;        // c1^c3 on bits 0,1,2
+  const uint32_t b = (z & M01) * 2u;               // c0^c2 on bit 1
+  const uint32_t s = (y & 0x07070707u) ^ a ^ b;    // 3-bit syndrome per byte
+  return __byte_perm(s | (s >> 4), 0u, 0x4420);    // low 16 bits: the four syndromes as PRMT selector nibbles
+}
 __device__ __forceinline__ Dec4 h84_decode4(uint32_t x) {
-  const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3, x4 = x >> 4, x5 = x >> 5, x6 = x >> 6;
-  const uint32_t s0 = (x ^ x1 ^ x3 ^ x4) & M01;
-  const uint32_t s1 = (x ^ x2 ^ x3 ^ x5) & M01;
-  const uint32_t s2 = (x1 ^ x2 ^ x3 ^ x6) & M01;
-  uint32_t t = x ^ x4;  // fold all 8 bits: stored parity vs recomputed parity
-  t ^= t >> 2;
-  t ^= t >> 1;
-  const uint32_t pe = t & M01;
-  const uint32_t s0p = s0 & pe;                 // only type 1 (syndrome!=0 & parity error) is corrected
-  const uint32_t f0 = s0p & s1 & ~s2;           // syndrome 3 -> d0
-  const uint32_t f1 = s0p & ~s1 & s2;           // syndrome 5 -> d1
-  const uint32_t f2 = ~s0 & s1 & s2 & pe;       // syndrome 6 -> d2
-  const uint32_t f3 = s0p & s1 & s2;            // syndrome 7 -> d3
+  uint32_t y;
+  const uint32_t sel = hamming_syndrome_sel(x, y);
+  const uint32_t t = y ^ (y >> 2);
   Dec4 r;
-  r.nib = (x & M0F) ^ (f0 | (f1 << 1) | (f2 << 2) | (f3 << 3));
-  r.nz = s0 | s1 | s2;
-  r.pe = pe;
+  r.pe = (t ^ (t >> 1)) & M01;
+  const uint32_t flip = __byte_perm(0x01000000u, 0x08040200u, sel);   // syndrome -> data-bit one-hot
+  r.nz = __byte_perm(0x01010100u, 0x01010101u, sel);
+  r.nib = (x & M0F) ^ (flip & (r.pe * 15u));      // only type 1 (syndrome != 0 and parity mismatch) is corrected
   return r;
 }
 // error type byte of hamming84_triton.py:185-187: 0 none, 1 single corrected, 2 double detected, 3 parity only
@@ -96,17 +100,17 @@ __device__ __forceinline__ uint32_t h84_double4(const Dec4& d) { return d.nz & ~
 
 // hamming74_triton.py:129-160: bit 7 is ignored, every non-zero syndrome is "corrected".
 __device__ __forceinline__ Dec4 h74_decode4(uint32_t x) {
-  const uint32_t x1 = x >> 1, x2 = x >> 2, x3 = x >> 3, x4 = x >> 4, x5 = x >> 5, x6 = x >> 6;
-  const uint32_t s0 = (x ^ x1 ^ x3 ^ x4) & M01;
-  const uint32_t s1 = (x ^ x2 ^ x3 ^ x5) & M01;
-  const uint32_t s2 = (x1 ^ x2 ^ x3 ^ x6) & M01;
-  const uint32_t f0 = s0 & s1 & ~s2, f1 = s0 & ~s1 & s2, f2 = ~s0 & s1 & s2, f3 = s0 & s1 & s2;
+  uint32_t y;
+  const uint32_t sel = hamming_syndrome_sel(x, y);
   Dec4 r;
-  r.nib = (x & M0F) ^ (f0 | (f1 << 1) | (f2 << 2) | (f3 << 3));
-  r.nz = s0 | s1 | s2;
+  r.nib = (x & M0F) ^ __byte_perm(0x01000000u, 0x08040200u, sel);
+  r.nz = __byte_perm(0x01010100u, 0x01010101u, sel);
   r.pe = 0;
   return r;
 }
+
+// sum of the four byte counters of a SWAR accumulator (each byte < 256)
+__device__ __forceinline__ uint32_t bytesum(uint32_t acc) { return (acc * M01) >> 24; }
 
 // 0x01-per-byte flag word -> 0xFF-per-byte select mask
 __device__ __forceinline__ uint32_t spread8(uint32_t f01) { return (f01 << 8) - f01; }

@@ -1,0 +1,135 @@
+#!/usr/bin/env python
+"""Per-kernel microbenchmarks (CUDA events on the launching stream, inputs >> L2): GB/s of algorithmic bytes and the
+fraction of the measured HBM peak, for every kernel of the path and the variants that matter (codec, injector,
+interpolation, dtype).  Usage: python tools/microbench.py [filter-substring ...]"""
+import json
+import statistics
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import torch  # noqa: E402
+
+from eccq_b200 import _lib  # noqa: E402
+from eccq_b200.ecc_codecs import cuda_kernels as ck  # noqa: E402
+from eccq_b200.kv_cache import SimpleBlockManager, paged_attention_ecc  # noqa: E402
+
+try:
+    PEAK = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+except Exception:
+    PEAK = 6650.0
+dev = torch.device("cuda", 0)
+lib = _lib.load()
+P = _lib.ptr
+SP = _lib.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+RESULTS = []
+
+
+def timeit(name, fn, nbytes, reps=20, warm=3):
+    if FILTERS and not any(f in name.replace(" ", "_") for f in FILTERS):
+        return
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = statistics.median(ts)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    RESULTS.append({"kernel": name, "ms": ms, "gbs": gbs, "frac": gbs / PEAK})
+    print(f"{name:58s} {ms:8.3f} ms {gbs:8.1f} GB/s  {100 * gbs / PEAK:5.1f}% of {PEAK:.0f}", flush=True)
+
+
+FILTERS = sys.argv[1:]
+N = 1 << 28  # 268 M codewords
+
+# ---- flat codecs
+x = torch.randint(0, 16, (N,), dtype=torch.uint8, device=dev)
+cw = ck.hamming84_encode(x)
+o1, o2 = torch.empty_like(x), torch.empty_like(x)
+ctr = _lib.new_counters(dev)
+timeit("h84_encode", lambda: lib.eccq_h84_encode(P(x), P(o1), N, SP), 2 * N)
+timeit("h74_encode", lambda: lib.eccq_h74_encode(P(x), P(o1), N, SP), 2 * N)
+noisy = ck.inject_bit_errors_fast(cw, 1e-2, 8, seed=1)
+timeit("h84_decode(data+etype)", lambda: lib.eccq_h84_decode(P(noisy), P(o1), P(o2), P(ctr), N, 0, SP), 3 * N)
+timeit("h84_decode(data only)", lambda: lib.eccq_h84_decode(P(noisy), P(o1), None, P(ctr), N, 0, SP), 2 * N)
+timeit("h74_decode(data+flag)", lambda: lib.eccq_h74_decode(P(noisy), P(o1), P(o2), P(ctr), N, SP), 3 * N)
+timeit("xor_mask_u8", lambda: lib.eccq_xor_mask(P(cw), P(noisy), P(o1), 1, 8, P(ctr), N, SP), 3 * N)
+for ber in (1e-2, 1e-3, 1e-4):
+    timeit(f"inject_philox_fast_u8 ber={ber}", lambda: lib.eccq_inject_philox_fast(P(cw), P(o1), 1, 8, ber, 42, P(ctr), N, SP), 2 * N)
+nref = 1 << 24
+timeit("inject_philox_ref_u8 (16M, compat)", lambda: lib.eccq_inject_philox_ref(P(cw), P(o1), None, 1, 8, 1e-2, 42, 0, P(ctr), nref, SP), 2 * nref)
+timeit("interpolate [ctx,1024]", lambda: lib.eccq_interpolate(P(x), P(o2), P(o1), 1, N // 1024, 1024, SP), 3 * N)
+del o2
+ncw = 90_177_536  # C4: Mistral [8,32768,8,128] -> 2 097 152 rows x 43 codewords
+trip = torch.randint(0, 16, (ncw * 3,), dtype=torch.uint8, device=dev)
+gcw = torch.empty(ncw, dtype=torch.int32, device=dev)
+lib.eccq_golay_encode(P(trip), P(gcw), ncw, SP)
+timeit("golay_encode (C4 size)", lambda: lib.eccq_golay_encode(P(trip), P(gcw), ncw, SP), 7 * ncw)
+gn = ck.inject_bit_errors_fast(gcw, 1e-2, 24, seed=2)
+gout = torch.empty(ncw * 3, dtype=torch.uint8, device=dev)
+gcnt = torch.empty(ncw, dtype=torch.uint8, device=dev)
+timeit("golay_decode (+count)", lambda: lib.eccq_golay_decode(P(gn), P(gout), P(gcnt), P(ctr), ncw, SP), 8 * ncw)
+timeit("golay_decode (data only)", lambda: lib.eccq_golay_decode(P(gn), P(gout), None, P(ctr), ncw, SP), 7 * ncw)
+timeit("inject_philox_fast_i32 ber=0.01", lambda: lib.eccq_inject_philox_fast(P(gcw), P(gn), 4, 24, 1e-2, 42, P(ctr), ncw, SP), 8 * ncw)
+del trip, gcw, gn, gout, gcnt, x, cw, noisy, o1
+
+# ---- fused cache write / read (C3 / C4 shapes)
+B, S, H, D, BS = 16, 8192, 8, 128, 16
+nblk = B * S // BS
+k = torch.randn(B, S, H * D, device=dev, dtype=torch.float16)
+v = torch.randn(B, S, H * D, device=dev, dtype=torch.float16)
+cl = torch.full((B,), S, dtype=torch.int32, device=dev)
+vals = 2 * B * S * H * D
+for codec in ("hamming84", "hamming74", "golay", "int4"):
+    m = SimpleBlockManager(nblk, BS, 1, H, D, device=dev, codec=codec)
+    m.block_table = torch.randperm(nblk).to(torch.int32).view(B, S // BS).to(dev)
+    desc = m.desc()
+    cwb = 4 * ((D + 2) // 3) / D if codec == "golay" else 1.0
+    wbytes = vals * (2 + cwb + 4 / D)
+    rbytes = vals * (cwb + 4 / D + 2)
+    for inj, ber in ((_lib.INJECT_NONE, 0.0), (_lib.INJECT_PHILOX_FAST, 1e-2), (_lib.INJECT_PHILOX_FAST, 1e-4)):
+        timeit(f"cache_write {codec} fp16 inject={inj} ber={ber}",
+               lambda: lib.eccq_cache_write(desc, P(k), P(v), _lib.ECCQ_F16, P(m.block_table), S // BS, None, B, S, 0, inj, None, None, ber, 42, 0,
+                                            P(ctr), SP), wbytes)
+    lib.eccq_cache_write(desc, P(k), P(v), _lib.ECCQ_F16, P(m.block_table), S // BS, None, B, S, 0, _lib.INJECT_PHILOX_FAST, None, None, 1e-2, 42, 0,
+                         P(ctr), SP)
+    ko = torch.empty(B, S, H, D, device=dev, dtype=torch.float16)
+    vo = torch.empty_like(ko)
+    for interp in ((0, 1) if codec == "hamming84" else (0,)):
+        timeit(f"cache_read {codec} fp16 interp={interp} (ber 1e-2 image)",
+               lambda: lib.eccq_cache_read(desc, P(m.block_table), S // BS, P(cl), B, S, 0, interp, _lib.ECCQ_F16, P(ko), P(vo), None, None, P(ctr), SP),
+               rbytes)
+    del ko, vo, m
+del k, v
+
+# ---- decode attention (C5 shard)
+Bq, ctx, HQ = 8, 32768, 32
+nblk = Bq * ctx // BS
+for codec in ("hamming84", "golay"):
+    m = SimpleBlockManager(nblk, BS, 1, H, D, device=dev, codec=codec)
+    m.block_table = torch.randperm(nblk).to(torch.int32).view(Bq, ctx // BS).to(dev)
+    for s0 in range(0, ctx, 4096):
+        kk = torch.randn(Bq, 4096, H * D, device=dev, dtype=torch.float16)
+        st = torch.full((Bq,), s0, dtype=torch.int32, device=dev)
+        lib.eccq_cache_write(m.desc(), P(kk), P(kk.flip(1)), _lib.ECCQ_F16, P(m.block_table), ctx // BS, P(st), Bq, 4096, 0, _lib.INJECT_PHILOX_FAST,
+                             None, None, 1e-3, 1, s0, None, SP)
+    q = torch.randn(Bq, HQ, D, device=dev, dtype=torch.float16)
+    cl = torch.full((Bq,), ctx, dtype=torch.int32, device=dev)
+    cwb = 4 * ((D + 2) // 3) if codec == "golay" else D
+    abytes = Bq * ctx * (2 * H * cwb + 2 * H * 4)
+    for interp in ((False, True) if codec == "hamming84" else (False,)):
+        timeit(f"decode_attention {codec} B8 ctx32k interp={int(interp)}",
+               lambda: paged_attention_ecc(q, m.k_cache, m.v_cache, m.block_table, cl, m.k_scales, 0, BS, codec=codec, v_scales=m.v_scales,
+                                           use_interpolation=interp), abytes, reps=10)
+    del m
+
+out = ROOT / "gpurun_out" / "microbench.json"
+out.parent.mkdir(exist_ok=True)
+out.write_text(json.dumps(RESULTS, indent=1))
