@@ -21,7 +21,7 @@ struct AttnArgs {
   float* ws;        // [nseq, Hq, nsplit, D + 2]  (acc[D], m, l)
   int max_blocks, nseq, Hq, layer, nsplit, chunk;
   float sm_scale;
-  int interp, v_use_k_scales, count_errors;
+  int interp, v_use_k_scales, count_errors, force_general;
 };
 
 constexpr int kAttnThreads = 256;
@@ -265,7 +265,7 @@ __global__ void attn_merge_kernel(const float* __restrict__ ws, TQ* __restrict__
 }
 
 static inline void attn_plan(int max_context, int& nsplit, int& chunk) {
-  chunk = 256;
+  chunk = 512;
   nsplit = (max_context + chunk - 1) / chunk;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > 128) { nsplit = 128; chunk = ((max_context + nsplit - 1) / nsplit + 15) / 16 * 16; }
@@ -304,8 +304,16 @@ static int dispatch_attn(const CacheGeom& g, const AttnArgs& a, uint64_t* counte
 }
 
 template <typename TQ>
+static int try_attn_mma(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st);  // eccq_attention_mma.cu
+
+template <typename TQ>
 static int run_attn(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
   int rc;
+  if (!a.force_general && try_attn_mma<TQ>(g, a, counters, st)) {
+    dim3 mg0(a.Hq, a.nseq);
+    attn_merge_kernel<TQ><<<mg0, 128, 0, st>>>(a.ws, reinterpret_cast<TQ*>(a.out), a.Hq, g.D, a.nsplit);
+    return ECCQ_OK;
+  }
   switch (g.codec) {
     case ECCQ_CODEC_H74: rc = dispatch_attn<TQ, ECCQ_CODEC_H74>(g, a, counters, st); break;
     case ECCQ_CODEC_H84: rc = dispatch_attn<TQ, ECCQ_CODEC_H84>(g, a, counters, st); break;
@@ -346,6 +354,7 @@ extern "C" int eccq_paged_decode_attention(const eccq_cache_desc* c, const void*
   AttnArgs a;
   a.q = q; a.out = out; a.block_table = block_table; a.context_lens = context_lens; a.ws = (float*)workspace;
   a.max_blocks = max_blocks; a.nseq = nseq; a.Hq = Hq; a.layer = layer; a.sm_scale = sm_scale;
+  a.force_general = getenv("ECCQ_ATTN_GENERAL") != nullptr;   // debugging aid: route everything through the general kernel
   a.interp = use_interpolation && g.codec == ECCQ_CODEC_H84; a.v_use_k_scales = v_use_k_scales; a.count_errors = count_errors && counters;
   attn_plan(max_blocks * g.bs, a.nsplit, a.chunk);
   if (workspace_bytes < (int64_t)nseq * Hq * a.nsplit * (g.D + 2) * (int64_t)sizeof(float))

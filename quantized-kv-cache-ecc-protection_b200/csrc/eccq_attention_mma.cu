@@ -1,0 +1,368 @@
+// eccq_attention_mma.cu -- ECC-fused paged decode attention, tensor-core tile version (v1).
+//
+// One CTA = (sequence, kv-head, context chunk), four warps; each warp walks 16-token tiles (one tile never straddles a
+// page: block_size % 16 == 0).  Per tile:
+//   cp.async   the K and V codeword rows of the tile (2 x 16 x D bytes) and their 2 x 16 fp32 scales are staged in shared
+//              memory one tile ahead (double buffer per warp), straight from the paged cache -- no gather pass;
+//   prologue   the codeword bytes are SWAR-decoded in registers (PRMT-LUT syndrome decode, eccq_common.cuh) and expanded
+//              to exact fp16 integers with the 0x6400|n magic (1024+n) minus 1032 -- the operands never exist in memory;
+//   QK^T       S^T[16 tokens x 8 heads] = K[16 x D] . Q^T on mma.sync m16n8k16 (A = K fragments built in registers with a
+//              dim permutation that makes every lane's bytes contiguous, B = Q fragments resident in registers);
+//   softmax    online, base 2 (log2e and sm_scale folded into Q), per-token K scale applied to S, V scale folded into P;
+//   PV         O^T[D x 8 heads] += V^T[D x 16 tokens] . P on mma.sync (P moved from accumulator to operand layout with
+//              movmatrix.trans; V fragments gathered across token rows with PRMT).
+// The GQA group (<= 8 q-heads) rides on the N dimension, so each codeword is decoded once for the whole group.
+// With fp32 queries Q and P are split hi+lo (two MMAs) so the 1e-4 bar of the reference's fp32 tests holds.
+//
+// This version issues legacy HMMA; the decode prologue (ALU pipe), not the tensor pipe, bounds it.  DESIGN.md describes
+// the tcgen05/TMEM variant that shares this staging and partial/merge protocol.
+#include "eccq_internal.h"
+
+namespace eccq {
+
+constexpr int kMmaWarps = 4;
+constexpr int kMmaThreads = kMmaWarps * 32;
+constexpr int kTile = 16;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+  uint32_t r;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+// two nibble bytes -> half2 of exact integers (n - 8): bytes {b, 0x64} = 1024 + n, then -1032
+__device__ __forceinline__ uint32_t nib2_to_half2(uint32_t w, uint32_t sel) {
+  const uint32_t h = __byte_perm(w, 0x64646464u, sel);
+  const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&h), __halves2half2(__ushort_as_half(0xE408), __ushort_as_half(0xE408)));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int CODEC, bool COUNT>
+__device__ __forceinline__ uint32_t decode_word(uint32_t w, uint32_t& ncorr, uint32_t& ndet) {
+  if (CODEC == ECCQ_CODEC_H84) {
+    const Dec4 d = h84_decode4(w);
+    if (COUNT) { ncorr += __popc(h84_single4(d)); ndet += __popc(h84_double4(d)); }
+    return d.nib;
+  }
+  if (CODEC == ECCQ_CODEC_H74) {
+    const Dec4 d = h74_decode4(w);
+    if (COUNT) ncorr += __popc(d.nz);
+    return d.nib;
+  }
+  return w;
+}
+
+template <typename TQ, int CODEC, int D, bool PRECISE, bool COUNT>
+__global__ void __launch_bounds__(kMmaThreads, 3) attn_mma_kernel(CacheGeom g, AttnArgs a, uint64_t* counters) {
+  constexpr int KS = D / 16;          // k-steps of QK^T == m-tiles of PV
+  constexpr int KW = D / 16;          // 32-bit words of a K row owned by a lane (D/4 bytes)
+  constexpr int VW = D / 32;          // words of a V row owned by a lane (D/8 bytes)
+  constexpr int ROW = D + 16;         // padded smem row stride: conflict-free 16-byte reads
+  constexpr int STAGE = 2 * kTile * ROW + 2 * kTile * 4;   // K rows, V rows, k scales, v scales
+  extern __shared__ __align__(16) unsigned char smem[];
+
+  const int split = blockIdx.x;
+  const int G = a.Hq / g.H;
+  const int npass = (G + 7) / 8;
+  const int h = blockIdx.y / npass;
+  const int pass = blockIdx.y - h * npass;
+  const int i = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grow = lane >> 2, quad = lane & 3;
+  const int ctx = a.context_lens[i];
+  const int c0 = split * a.chunk;
+  const int c1 = min(ctx, c0 + a.chunk);
+  const int g0 = pass * 8;
+  const int ng = min(8, G - g0);
+  const int32_t* bt = a.block_table + (int64_t)i * a.max_blocks;
+  const int64_t page_bytes = (int64_t)g.bs * D;
+  unsigned char* wsm = smem + (size_t)warp * 2 * STAGE;
+  const float* vsc_base = a.v_use_k_scales ? g.k_scales : g.v_scales;
+
+  // ---- Q fragments (B operand of QK^T): head n = lane/4, dims quad*(D/4) + 4s + {0,1 | 2,3}; sm_scale*log2e folded in
+  uint32_t qf[KS][2], qf_lo[PRECISE ? KS : 1][2];
+  {
+    const bool valid = grow < ng;
+    const int64_t qbase = ((int64_t)i * a.Hq + (int64_t)h * G + g0 + (valid ? grow : 0)) * D;
+    const float sc = a.sm_scale * 1.4426950408889634f;
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = valid ? ldq<TQ>(a.q, qbase + quad * (D / 4) + 4 * s + e) * sc : 0.0f;
+      qf[s][0] = pack_half2(v[0], v[1]);
+      qf[s][1] = pack_half2(v[2], v[3]);
+      if (PRECISE) {
+        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&qf[s][0]));
+        const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&qf[s][1]));
+        qf_lo[s][0] = pack_half2(v[0] - h0.x, v[1] - h0.y);
+        qf_lo[s][1] = pack_half2(v[2] - h1.x, v[3] - h1.y);
+      }
+    }
+  }
+
+  float o[KS][4];
+#pragma unroll
+  for (int mt = 0; mt < KS; ++mt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[mt][e] = 0.0f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};   // heads 2*quad, 2*quad+1
+  uint32_t ncorr = 0, ndet = 0;
+  const bool do_count = COUNT && pass == 0;
+
+  // tiles of this warp: first tile index (in units of 16 tokens) is c0/16 + warp, stride kMmaWarps
+  const int tile_end = (c1 + kTile - 1) / kTile;
+  auto stage_tile = [&](int tile, int st) {
+    unsigned char* dst = wsm + (size_t)st * STAGE;
+    const int tok0 = tile * kTile;
+    const int lb = tok0 / g.bs;
+    const int blk = bt[lb];
+    if (blk >= 0) {
+      const int64_t page = page_index(g, blk, a.layer, h);
+      const int slot0 = tok0 - lb * g.bs;
+      const uint8_t* ksrc = g.k_cache + page * page_bytes + (int64_t)slot0 * D;
+      const uint8_t* vsrc = g.v_cache + page * page_bytes + (int64_t)slot0 * D;
+#pragma unroll
+      for (int j = 0; j < kTile * D / 16 / 32; ++j) {
+        const int c = lane + 32 * j;
+        const int row = c / (D / 16), col = c % (D / 16);
+        cp_async16(dst + row * ROW + col * 16, ksrc + row * D + col * 16);
+        cp_async16(dst + kTile * ROW + row * ROW + col * 16, vsrc + row * D + col * 16);
+      }
+      if (lane < 4) cp_async16(dst + 2 * kTile * ROW + lane * 16, g.k_scales + page * g.bs + slot0 + lane * 4);
+      else if (lane < 8) cp_async16(dst + 2 * kTile * ROW + kTile * 4 + (lane - 4) * 16, vsc_base + page * g.bs + slot0 + (lane - 4) * 4);
+    }
+    return blk >= 0;
+  };
+
+  int tile = c0 / kTile + warp;
+  bool cur_ok = false;
+  if (tile < tile_end) cur_ok = stage_tile(tile, 0);
+  cp_async_commit();
+  int st = 0;
+  for (; tile < tile_end; tile += kMmaWarps, st ^= 1) {
+    const int ntile = tile + kMmaWarps;
+    bool next_ok = false;
+    if (ntile < tile_end) next_ok = stage_tile(ntile, st ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    if (cur_ok) {
+      const unsigned char* sK = wsm + (size_t)st * STAGE;
+      const unsigned char* sV = sK + kTile * ROW;
+      const float* sKs = reinterpret_cast<const float*>(sK + 2 * kTile * ROW);
+      const float* sVs = sKs + kTile;
+      const int tok0 = tile * kTile;
+
+      // ---------------- QK^T: rows grow and grow+8, this lane's D/4 bytes of each
+      float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      {
+        uint32_t kr0[KW], kr1[KW];
+#pragma unroll
+        for (int w4 = 0; w4 < KW / 4; ++w4) {
+          const uint4 x0 = *reinterpret_cast<const uint4*>(sK + grow * ROW + quad * (D / 4) + 16 * w4);
+          const uint4 x1 = *reinterpret_cast<const uint4*>(sK + (grow + 8) * ROW + quad * (D / 4) + 16 * w4);
+          kr0[4 * w4] = x0.x; kr0[4 * w4 + 1] = x0.y; kr0[4 * w4 + 2] = x0.z; kr0[4 * w4 + 3] = x0.w;
+          kr1[4 * w4] = x1.x; kr1[4 * w4 + 1] = x1.y; kr1[4 * w4 + 2] = x1.z; kr1[4 * w4 + 3] = x1.w;
+        }
+        const bool v0 = do_count && tok0 + grow < c1, v1 = do_count && tok0 + grow + 8 < c1;
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+          uint32_t cc = 0, dd = 0;
+          const uint32_t n0 = decode_word<CODEC, COUNT>(kr0[s], cc, dd);
+          if (COUNT && v0) { ncorr += cc; ndet += dd; }
+          cc = dd = 0;
+          const uint32_t n1 = decode_word<CODEC, COUNT>(kr1[s], cc, dd);
+          if (COUNT && v1) { ncorr += cc; ndet += dd; }
+          const uint32_t af[4] = {nib2_to_half2(n0, 0x4140), nib2_to_half2(n1, 0x4140), nib2_to_half2(n0, 0x4342), nib2_to_half2(n1, 0x4342)};
+          mma16816(s4, af, qf[s][0], qf[s][1]);
+          if (PRECISE) mma16816(s4, af, qf_lo[s][0], qf_lo[s][1]);
+        }
+      }
+      // ---------------- scale, mask, online softmax (heads 2*quad, 2*quad+1; tokens grow, grow+8)
+      const float ks0 = sKs[grow], ks1 = sKs[grow + 8];
+      const bool t0ok = tok0 + grow < c1, t1ok = tok0 + grow + 8 < c1;
+      s4[0] = t0ok ? s4[0] * ks0 : -INFINITY; s4[1] = t0ok ? s4[1] * ks0 : -INFINITY;
+      s4[2] = t1ok ? s4[2] * ks1 : -INFINITY; s4[3] = t1ok ? s4[3] * ks1 : -INFINITY;
+      float mx[2] = {fmaxf(s4[0], s4[2]), fmaxf(s4[1], s4[3])};
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+        mx[0] = fmaxf(mx[0], __shfl_xor_sync(0xFFFFFFFFu, mx[0], off));
+        mx[1] = fmaxf(mx[1], __shfl_xor_sync(0xFFFFFFFFu, mx[1], off));
+      }
+      float alpha[2], p[4];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float mn = fmaxf(m_run[e], mx[e]);
+        alpha[e] = (mn == -INFINITY) ? 1.0f : exp2f(m_run[e] - mn);
+        m_run[e] = mn;
+      }
+      p[0] = (m_run[0] == -INFINITY) ? 0.0f : exp2f(s4[0] - m_run[0]);
+      p[1] = (m_run[1] == -INFINITY) ? 0.0f : exp2f(s4[1] - m_run[1]);
+      p[2] = (m_run[0] == -INFINITY) ? 0.0f : exp2f(s4[2] - m_run[0]);
+      p[3] = (m_run[1] == -INFINITY) ? 0.0f : exp2f(s4[3] - m_run[1]);
+      l_run[0] = l_run[0] * alpha[0] + p[0] + p[2];   // per-lane partial sums; reduced over the 8 row-lanes at the end
+      l_run[1] = l_run[1] * alpha[1] + p[1] + p[3];
+#pragma unroll
+      for (int mt = 0; mt < KS; ++mt) { o[mt][0] *= alpha[0]; o[mt][1] *= alpha[1]; o[mt][2] *= alpha[0]; o[mt][3] *= alpha[1]; }
+      // ---------------- P (x V scale) -> B fragments of PV
+      const float vs0 = sVs[grow], vs1 = sVs[grow + 8];
+      const float pv[4] = {p[0] * vs0, p[1] * vs0, p[2] * vs1, p[3] * vs1};
+      const uint32_t ph0 = pack_half2(pv[0], pv[1]), ph1 = pack_half2(pv[2], pv[3]);
+      const uint32_t pb0 = movmatrix_trans(ph0), pb1 = movmatrix_trans(ph1);
+      uint32_t pl0 = 0, pl1 = 0;
+      if (PRECISE) {
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&ph0));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&ph1));
+        pl0 = movmatrix_trans(pack_half2(pv[0] - f0.x, pv[1] - f0.y));
+        pl1 = movmatrix_trans(pack_half2(pv[2] - f1.x, pv[3] - f1.y));
+      }
+      // ---------------- PV: tokens 2q, 2q+1, 2q+8, 2q+9; this lane's D/8 bytes [grow*D/8, +D/8) of each
+      {
+        uint32_t vr[4][VW];
+        const int toks[4] = {2 * quad, 2 * quad + 1, 2 * quad + 8, 2 * quad + 9};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const unsigned char* src = sV + toks[t] * ROW + grow * (D / 8);
+          if (VW == 4) {
+            const uint4 x = *reinterpret_cast<const uint4*>(src);
+            vr[t][0] = x.x; vr[t][1] = x.y; vr[t][2 % VW] = x.z; vr[t][3 % VW] = x.w;
+          } else {
+            const uint2 x = *reinterpret_cast<const uint2*>(src);
+            vr[t][0] = x.x; vr[t][1 % VW] = x.y;
+          }
+          const bool vok = do_count && tok0 + toks[t] < c1;
+#pragma unroll
+          for (int w = 0; w < VW; ++w) {
+            uint32_t cc = 0, dd = 0;
+            vr[t][w] = decode_word<CODEC, COUNT>(vr[t][w], cc, dd);
+            if (COUNT && vok) { ncorr += cc; ndet += dd; }
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < KS; ++mt) {
+          const int w = mt >> 1;
+          const uint32_t sel = (mt & 1) ? 0x7362u : 0x5140u;
+          const uint32_t x01 = __byte_perm(vr[0][w], vr[1][w], sel);   // {T0.b, T1.b, T0.b+1, T1.b+1}
+          const uint32_t x23 = __byte_perm(vr[2][w], vr[3][w], sel);
+          const uint32_t af[4] = {nib2_to_half2(x01, 0x4140), nib2_to_half2(x01, 0x4342), nib2_to_half2(x23, 0x4140), nib2_to_half2(x23, 0x4342)};
+          mma16816(o[mt], af, pb0, pb1);
+          if (PRECISE) mma16816(o[mt], af, pl0, pl1);
+        }
+      }
+    }
+    __syncwarp();
+    cur_ok = next_ok;
+  }
+  cp_async_wait<0>();
+
+  // ---- reduce the row sums over the 8 row-lanes (m_run is already uniform across them)
+#pragma unroll
+  for (int off = 4; off < 32; off <<= 1) {
+    l_run[0] += __shfl_xor_sync(0xFFFFFFFFu, l_run[0], off);
+    l_run[1] += __shfl_xor_sync(0xFFFFFFFFu, l_run[1], off);
+  }
+  // ---- merge the four warps through shared memory (reuse the staging area), write the chunk partial
+  __syncthreads();
+  constexpr int RS = D + 2;
+  float* red = reinterpret_cast<float*>(smem);            // [warp][8 heads][D + 2]
+  {
+    float* dst = red + (size_t)warp * 8 * RS;
+#pragma unroll
+    for (int mt = 0; mt < KS; ++mt) {
+      const int d0 = grow * (D / 8) + 2 * mt;              // rows grow / grow+8 of m-tile mt -> dims d0 / d0+1
+      dst[(2 * quad) * RS + d0] = o[mt][0];
+      dst[(2 * quad + 1) * RS + d0] = o[mt][1];
+      dst[(2 * quad) * RS + d0 + 1] = o[mt][2];
+      dst[(2 * quad + 1) * RS + d0 + 1] = o[mt][3];
+    }
+    if (grow == 0) {
+      dst[(2 * quad) * RS + D] = m_run[0]; dst[(2 * quad) * RS + D + 1] = l_run[0];
+      dst[(2 * quad + 1) * RS + D] = m_run[1]; dst[(2 * quad + 1) * RS + D + 1] = l_run[1];
+    }
+  }
+  __syncthreads();
+  for (int gi = warp; gi < ng; gi += kMmaWarps) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kMmaWarps; ++w) M = fmaxf(M, red[((size_t)w * 8 + gi) * RS + D]);
+    float f[kMmaWarps], L = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kMmaWarps; ++w) {
+      const float mw = red[((size_t)w * 8 + gi) * RS + D];
+      f[w] = (mw == -INFINITY) ? 0.0f : exp2f(mw - M);
+      L += red[((size_t)w * 8 + gi) * RS + D + 1] * f[w];
+    }
+    const int qh = h * G + g0 + gi;
+    float* wsrow = a.ws + (((int64_t)i * a.Hq + qh) * a.nsplit + split) * (D + 2);
+    for (int d = lane; d < D; d += 32) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kMmaWarps; ++w) acc += red[((size_t)w * 8 + gi) * RS + d] * f[w];
+      wsrow[d] = acc;
+    }
+    // the merge kernel works in natural-log units: m_ln = m_log2 * ln2
+    if (lane == 0) { wsrow[D] = (M == -INFINITY) ? -INFINITY : M * 0.6931471805599453f; wsrow[D + 1] = L; }
+  }
+  if (COUNT) {
+    const int idx[2] = {ECCQ_CTR_CORRECTED, ECCQ_CTR_DETECTED};
+    const uint32_t val[2] = {ncorr, ndet};
+    block_accumulate<2>(counters, idx, val);
+  }
+}
+
+template <typename TQ, int CODEC, int D, bool PRECISE>
+static int launch_attn_mma(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  const size_t stage = 2 * kTile * (D + 16) + 2 * kTile * 4;
+  const size_t smem = std::max<size_t>(kMmaWarps * 2 * stage, sizeof(float) * kMmaWarps * 8 * (D + 2));
+  const int G = a.Hq / g.H;
+  const int npass = (G + 7) / 8;
+  dim3 grid(a.nsplit, g.H * npass, a.nseq);
+  if (a.count_errors) {
+    auto kern = attn_mma_kernel<TQ, CODEC, D, PRECISE, true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kMmaThreads, smem, st>>>(g, a, counters);
+  } else {
+    auto kern = attn_mma_kernel<TQ, CODEC, D, PRECISE, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kMmaThreads, smem, st>>>(g, a, counters);
+  }
+  return ECCQ_OK;
+}
+
+// returns 1 when the tile kernel took the launch, 0 when the shape/codec needs the general kernel
+template <typename TQ>
+static int try_attn_mma(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  if (g.codec == ECCQ_CODEC_GOLAY || a.interp) return 0;
+  if ((g.D != 64 && g.D != 128) || g.bs % kTile != 0 || a.chunk % kTile != 0) return 0;
+  if (!aligned16(g.k_cache) || !aligned16(g.v_cache) || !aligned16(g.k_scales) || !aligned16(g.v_scales)) return 0;
+  constexpr bool PRECISE = sizeof(TQ) == 4;
+#define ECCQ_MMA_CASE(C)                                                                       \
+  if (g.D == 128) launch_attn_mma<TQ, C, 128, PRECISE>(g, a, counters, st);                    \
+  else launch_attn_mma<TQ, C, 64, PRECISE>(g, a, counters, st);                                \
+  return 1
+  switch (g.codec) {
+    case ECCQ_CODEC_H84: ECCQ_MMA_CASE(ECCQ_CODEC_H84);
+    case ECCQ_CODEC_H74: ECCQ_MMA_CASE(ECCQ_CODEC_H74);
+    default: ECCQ_MMA_CASE(ECCQ_CODEC_INT4);
+  }
+#undef ECCQ_MMA_CASE
+}
+
+}  // namespace eccq

@@ -24,6 +24,7 @@ int ensure_tables() {
 #include "eccq_codecs.cu"
 #include "eccq_cache.cu"
 #include "eccq_attention.cu"
+#include "eccq_attention_mma.cu"
 
 extern "C" int eccq_abi_version(void) { return ECCQ_ABI_VERSION; }
 extern "C" const char* eccq_last_error(void) { return eccq::last_error_ref(); }
