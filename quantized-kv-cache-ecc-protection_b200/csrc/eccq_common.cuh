@@ -64,39 +64,47 @@ __device__ __forceinline__ uint32_t h84_encode4(uint32_t x) {
 struct Dec4 {
   uint32_t nib;  // corrected nibbles, one per byte
   uint32_t nz;   // 0x01 per byte: syndrome != 0
-  uint32_t pe;   // 0x01 per byte: overall-parity mismatch (Hamming(8,4) only)
+  uint32_t pm;   // 0xFF per byte: overall-parity mismatch (Hamming(8,4) only)
 };
 
 // Syndrome decode of hamming84_triton.py:116-209 on four codeword bytes at once.
-//   y = x ^ x>>4 folds the parity nibble onto the data nibble (y_i = c_i ^ c_{i+4}), z = x ^ x>>2 gives c0^c2 / c1^c3, so
-//   s0 = y0^(c1^c3), s1 = y1^(c0^c2)^(c1^c3), s2 = y2^(c1^c3), overall parity mismatch pe = y0^y1^y2^y3.
+//   y = x ^ x<<4 folds the data nibble onto the parity nibble (bit 4+i = c_i ^ c_{i+4}), z = x ^ x<<2 gives c0^c2 (bit 2)
+//   and c1^c3 (bit 3), so on bits 4,5,6:  s0 = y0^(c1^c3), s1 = y1^(c0^c2)^(c1^c3), s2 = y2^(c1^c3);
+//   overall parity mismatch = y0^y1^y2^y3 lands on bit 7.
+//   Only LEFT shifts and constant multiplies are used to build these: they issue as IMAD/IMAD.SHL on the FMA pipe and keep
+//   the ALU pipe -- the bottleneck of every decode-side kernel here -- for the boolean work.
 //   The 8-entry syndrome table [-1,4,5,0,6,1,2,3] (config.py:131-161) only reaches a DATA bit for syndromes 3,5,6,7
 //   (bits 0..3); it is applied as a register-resident byte LUT through PRMT: the four 3-bit syndromes are packed into one
-//   selector and index the 8-byte table {0,0,0,1,0,2,4,8} (and {0,1,1,1,1,1,1,1} for "syndrome != 0").
-//   The 0/1 masks are widened with IMAD (FMA pipe) to keep the ALU pipe, the bottleneck of these kernels, lighter.
+//   selector and index the 8-byte tables {0,0,0,1,0,2,4,8} (bit to flip) and {0,1,1,1,1,1,1,1} (syndrome != 0).
+//   PRMT's sign-replicate mode turns the parity bit into the 0xFF/0x00 byte mask that gates the correction
+//   (only "syndrome != 0 AND parity mismatch" = single error is corrected; double errors keep the raw nibble).
 __device__ __forceinline__ uint32_t hamming_syndrome_sel(uint32_t x, uint32_t& y) {
-  y = x ^ (x >> 4);
-  const uint32_t z = x ^ (x >> 2);
-  const uint32_t a = ((z >> 1) & M01) * 7u;        // c1^c3 on bits 0,1,2
-  const uint32_t b = (z & M01) * 2u;               // c0^c2 on bit 1
-  const uint32_t s = (y & 0x07070707u) ^ a ^ b;    // 3-bit syndrome per byte
-  return __byte_perm(s | (s >> 4), 0u, 0x4420);    // low 16 bits: the four syndromes as PRMT selector nibbles
+  y = x ^ (x * 16u);
+  const uint32_t z = x ^ (x * 4u);
+  const uint32_t a = (z & 0x08080808u) * 14u;      // c1^c3 on bits 4,5,6
+  const uint32_t b = (z & 0x04040404u) * 8u;       // c0^c2 on bit 5
+  const uint32_t s = (y & 0x70707070u) ^ a ^ b;    // 3-bit syndrome on bits 4..6 of each byte
+  const uint32_t u = s >> 4;
+  return __byte_perm(u | (u >> 4), 0u, 0x4420);    // low 16 bits: the four syndromes as PRMT selector nibbles
 }
 __device__ __forceinline__ Dec4 h84_decode4(uint32_t x) {
   uint32_t y;
   const uint32_t sel = hamming_syndrome_sel(x, y);
-  const uint32_t t = y ^ (y >> 2);
+  const uint32_t t = y ^ (y * 4u);
+  const uint32_t pe = (t ^ (t * 2u)) & 0x80808080u;
   Dec4 r;
-  r.pe = (t ^ (t >> 1)) & M01;
+  // msb -> 0xFF / 0x00 per byte: selector nibbles 8|i = "replicate the sign of byte i" (raw prmt; __byte_perm only
+  // documents the low three selector bits)
+  asm("prmt.b32 %0, %1, %2, 0xBA98;" : "=r"(r.pm) : "r"(pe), "r"(0u));
   const uint32_t flip = __byte_perm(0x01000000u, 0x08040200u, sel);   // syndrome -> data-bit one-hot
   r.nz = __byte_perm(0x01010100u, 0x01010101u, sel);
-  r.nib = (x & M0F) ^ (flip & (r.pe * 15u));      // only type 1 (syndrome != 0 and parity mismatch) is corrected
+  r.nib = (x & M0F) ^ (flip & r.pm);
   return r;
 }
 // error type byte of hamming84_triton.py:185-187: 0 none, 1 single corrected, 2 double detected, 3 parity only
-__device__ __forceinline__ uint32_t h84_etype4(const Dec4& d) { return d.pe | ((d.nz ^ d.pe) << 1); }
-__device__ __forceinline__ uint32_t h84_single4(const Dec4& d) { return d.nz & d.pe; }
-__device__ __forceinline__ uint32_t h84_double4(const Dec4& d) { return d.nz & ~d.pe; }
+__device__ __forceinline__ uint32_t h84_etype4(const Dec4& d) { const uint32_t pe = d.pm & M01; return pe | ((d.nz ^ pe) << 1); }
+__device__ __forceinline__ uint32_t h84_single4(const Dec4& d) { return d.nz & d.pm; }
+__device__ __forceinline__ uint32_t h84_double4(const Dec4& d) { return d.nz & ~d.pm; }
 
 // hamming74_triton.py:129-160: bit 7 is ignored, every non-zero syndrome is "corrected".
 __device__ __forceinline__ Dec4 h74_decode4(uint32_t x) {
@@ -105,7 +113,7 @@ __device__ __forceinline__ Dec4 h74_decode4(uint32_t x) {
   Dec4 r;
   r.nib = (x & M0F) ^ __byte_perm(0x01000000u, 0x08040200u, sel);
   r.nz = __byte_perm(0x01010100u, 0x01010101u, sel);
-  r.pe = 0;
+  r.pm = 0;
   return r;
 }
 
