@@ -4,7 +4,7 @@ Generate the golden fixtures in this directory from the REFERENCE ITSELF.
 
 Run in the authoring container only (needs /root/reference, never the GPU box):
 
-    TRITON_INTERPRET=1 python tests/golden/make_golden.py
+    TRITON_INTERPRET=1 python tests/golden/make_golden.py [core] [gpt2]
 
 The reference's @triton.jit kernels execute on CPU tensors under the Triton interpreter.  Its
 Python wrappers assert ``tensor.is_cuda``; we re-exec each wrapper's source with that one line
@@ -61,8 +61,8 @@ def _strip_cuda_asserts():
     return h74, h84, gol, fi, ip, att, shim, pc
 
 
-def main():
-    h74, h84, gol, fi, ip, att, shim, pc = _strip_cuda_asserts()
+def core_sections(mods):
+    h74, h84, gol, fi, ip, att, shim, pc = mods
     from ecc_codecs.triton_kernels.config import build_golay_syndrome_table, GOLAY_H_ROW_MASKS
 
     rng = np.random.default_rng(20251018)
@@ -249,6 +249,46 @@ def main():
     at.update(g_q=qg, g_k_cache=gk.numpy(), g_v_cache=gv.numpy(), g_out=o_g.numpy(), g_dims=np.array([Dg, ncw], dtype=np.int64))
     np.savez_compressed(OUT / "attention_vectors.npz", **at)
 
+
+
+def gpt2_section(mods):
+    """Config 2 in miniature: a random-init 2-layer GPT-2 under patch_model_with_ecc_attention on CPU, every ECC mode,
+    BER 0 and 1e-2 (evaluation/sweep.py:512-590 call pattern: reset_ecc_cache, forward with labels, get_ecc_stats)."""
+    shim = mods[6]
+    from transformers import GPT2Config, GPT2LMHeadModel
+    torch.manual_seed(1234)
+    cfg = GPT2Config(n_layer=2, n_head=2, n_embd=32, vocab_size=100, n_positions=64, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    model = GPT2LMHeadModel(cfg).eval()
+    ids = torch.randint(0, 100, (1, 24), generator=torch.Generator().manual_seed(5))
+    out = {"input_ids": ids.numpy()}
+    for k, v in model.state_dict().items():
+        out["w::" + k] = v.numpy()
+    with torch.no_grad():
+        out["baseline_logits"] = model(ids).logits.numpy()
+    for codec, interp in (("hamming74", False), ("hamming84", False), ("hamming84", True), ("golay", False)):
+        for ber in (0.0, 1e-2):
+            tag = f"{codec}{'_interp' if interp else ''}_ber{ber}"
+            c = shim.ECCShimConfig(codec=codec, ber=ber, inject_errors=ber > 0, seed=42, use_interpolation=interp, block_size=16, num_blocks=8)
+            with shim.patch_model_with_ecc_attention(model, c, num_blocks=8):
+                shim.reset_ecc_cache(model)
+                with torch.no_grad():
+                    r = model(ids, labels=ids)
+                st = shim.get_ecc_stats(model)
+            out[tag + "_logits"] = r.logits.numpy()
+            out[tag + "_loss"] = np.float64(r.loss.item())
+            out[tag + "_stats"] = np.array([st["injection_count"], st["errors_corrected"], st["errors_detected"], st["total_values"],
+                                            st["allocated_blocks"], st["free_blocks"], st["sequences"]], dtype=np.int64)
+            print(tag, float(r.loss), st)
+    np.savez_compressed(OUT / "gpt2_shim_vectors.npz", **out)
+
+
+def main():
+    sel = set(sys.argv[1:])
+    mods = _strip_cuda_asserts()
+    if not sel or "core" in sel:
+        core_sections(mods)
+    if not sel or "gpt2" in sel:
+        gpt2_section(mods)
     print("golden fixtures written to", OUT)
     for f in sorted(OUT.glob("*.npz")):
         print(f"  {f.name:28s} {f.stat().st_size:8d} B")
