@@ -224,6 +224,7 @@ __device__ __forceinline__ uint32_t ref_flip_mask_vec(uint32_t seed_lo, uint32_t
 // One Philox call = 4 gaps; expected calls per chunk = ceil((1 + npos*p)/4).  `hit(pos)` is invoked per flip.
 struct FastInject {
   float inv_lg2_q;  // 1 / log2(1-p)  (negative); 0 => p >= 1 (flip everything)
+  float ber;
   uint32_t seed_lo, seed_hi;
 };
 template <class Hit>

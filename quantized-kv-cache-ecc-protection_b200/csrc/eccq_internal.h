@@ -102,6 +102,7 @@ inline FastInject make_fast_inject(float ber, uint64_t seed) {
   FastInject fi;
   fi.seed_lo = (uint32_t)seed;
   fi.seed_hi = (uint32_t)(seed >> 32);
+  fi.ber = ber;
   fi.inv_lg2_q = ber >= 1.0f ? 0.0f : (float)(1.0 / std::log2(1.0 - (double)ber));
   return fi;
 }
