@@ -117,6 +117,87 @@ __device__ __forceinline__ Dec4 h74_decode4(uint32_t x) {
   return r;
 }
 
+// ------------------------------------------------------------------------------------------------ Hamming, second formulation
+// Pipe rates measured on B200 (tools/pipe_bench.cu): LOP3/PRMT/SHF/F2FP issue at 0.5 warp-instr/clk/SMSP (ALU pipe),
+// IMAD/IDP.4A at 0.5 (FMA-heavy pipe), FP32 FFMA/FMUL/FADD/FHADD at ~0.93, and ALU+FMA co-issue reaches ~0.96.  The codec
+// kernels are bound by the ALU pipe, so this formulation minimises ALU operations: 11 per four codewords (the first one
+// needs 19) + 7 IMAD, with the flags counted by two IDP.4A.
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+  return d;
+}
+constexpr int kLopXorAnd = 0x28;   // (a ^ b) & c
+constexpr int kLopXor3 = 0x96;     // a ^ b ^ c
+constexpr int kLopSelect = 0xD8;   // a ^ ((a ^ b) & c) = c ? b : a
+// raw PRMT: selector nibble bit 3 = "replicate the sign of the selected byte" (0xFF / 0x00)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// Four codewords -> PRMT selector with one nibble per codeword: bits [2:0] = an invertible linear image of the syndrome,
+//   i = s0 + 2 (s0^s1) + 4 (s0^s1^s2),  bit 3 = NOT(overall parity mismatch)  (Hamming(7,4): bit 3 = 0).
+// With c_j the bits of a byte, yc = (x ^ x<<4) & 0xF0 folds data onto parity (bit 4+j = c_{4+j}^c_j), z = x ^ x<<2 gives
+// u = c1^c3 (bit 3) and v = c0^c2 (bit 2).  W = yc ^ yc<<2 ^ u*0x30 ^ v*0x20 (^ 0x80) has bit4 = s0, bit5 = s1,
+// bit6 = s0^s2 = y4^y6, bit7 = NOT(y5^y7); one more fold W ^ W<<1 yields the nibble above on bits 4..7 of every byte with
+// the low nibble cleared, so the four nibbles pack with ONE multiply (x17: bytes 1 and 3 become the nibble pairs).
+// Left shifts / multiplies issue as IMAD on the FMA pipe.
+template <int CODEC>
+__device__ __forceinline__ uint32_t hamming_sel4(uint32_t x) {
+  constexpr uint32_t keep = CODEC == ECCQ_CODEC_H84 ? 0xF0F0F0F0u : 0x70707070u;
+  const uint32_t yc = lop3<kLopXorAnd>(x, x * 16u, keep);
+  const uint32_t z = x ^ (x * 4u);
+  const uint32_t a2 = (z & 0x08080808u) * 6u + (CODEC == ECCQ_CODEC_H84 ? 0x80808080u : 0u);
+  const uint32_t b2 = (z & 0x04040404u) * 8u;
+  const uint32_t w = lop3<kLopXor3>(yc ^ (yc * 4u), a2, b2);
+  const uint32_t selw = lop3<kLopXorAnd>(w, w * 2u, keep);
+  return prmt(selw * 17u, 0u, 0x4431u);
+}
+// flip one-hot of the data bit per index i (0 for parity-bit syndromes); every byte has MSB 0, so in sign-replicate mode
+// (parity matches: clean or double error) the lookup returns 0 and nothing is corrected.
+constexpr uint32_t kFlipLutLo = 0x02040100u, kFlipLutHi = 0x00000800u;
+// flag byte: 0x00 syndrome 0 (clean / parity-bit only), 0x80 single error corrected, 0xFF double error detected
+// (entries 0x80 for i != 0: read as is when the parity mismatches, sign-replicated to 0xFF when it matches).
+constexpr uint32_t kFlagLutLo = 0x80808000u, kFlagLutHi = 0x80808080u;
+
+// hamming84_triton.py:116-209 / hamming74_triton.py:129-160 on four codewords: nib = corrected nibbles (one per byte,
+// double errors keep the raw nibble), flag as above (Hamming(7,4): 0x80 = corrected, never 0xFF).
+template <int CODEC>
+__device__ __forceinline__ void hamming_decode4(uint32_t x, uint32_t& nib, uint32_t& flag) {
+  const uint32_t sel = hamming_sel4<CODEC>(x);
+  const uint32_t flip = prmt(kFlipLutLo, kFlipLutHi, sel);
+  flag = prmt(kFlagLutLo, kFlagLutHi, sel);
+  nib = lop3<kLopXorAnd>(x, flip, M0F);
+}
+// flag bytes are 0x80 (single) / 0xFF (double): unsigned byte sum = 128 ns + 255 nd, signed byte sum = -128 ns - nd
+struct FlagCount {
+  uint32_t tu = 0;
+  int32_t ts = 0;
+  __device__ __forceinline__ void add(uint32_t flag) {
+    tu = __dp4a(flag, 0x01010101u, tu);
+    ts = __dp4a((int32_t)flag, (int32_t)0x01010101, ts);
+  }
+  __device__ __forceinline__ uint32_t doubles() const { return (uint32_t)((int32_t)tu + ts) / 254u; }
+  __device__ __forceinline__ uint32_t singles() const { return (tu - 255u * doubles()) >> 7; }
+};
+// error type byte of hamming84_triton.py:185-187 from (flag, parity): 0 none, 1 single, 2 double, 3 parity bit only
+// (only the flat decode kernel materialises it)
+
+// Encode four nibbles given as a PRMT selector (nibble e = value e): codeword(n) = LUT8[n & 7] ^ (n & 8 ? 0x78 : 0)
+// (generator row of data bit 3 is 0x78 for both Hamming codes).  5 ALU operations per four codewords.
+template <int CODEC>
+__device__ __forceinline__ uint32_t hamming_encode_sel4(uint32_t sel) {
+  constexpr uint32_t lo = CODEC == ECCQ_CODEC_H84 ? 0x63D2B100u : 0x63523100u;   // codewords of 0..3
+  constexpr uint32_t hi = CODEC == ECCQ_CODEC_H84 ? 0x873655E4u : 0x07365564u;   // codewords of 4..7
+  const uint32_t low = prmt(lo, hi, sel & 0x7777u);
+  // selector nibble 8 -> sign of 0x80 replicated (0xFF), nibble 0 -> the byte 0x80 itself; "& 0x78" leaves 0x78 / 0
+  const uint32_t top = prmt(0x80u, 0u, sel & 0x8888u);
+  return low ^ (top & 0x78787878u);
+}
+
 // sum of the four byte counters of a SWAR accumulator (each byte < 256)
 __device__ __forceinline__ uint32_t bytesum(uint32_t acc) { return (acc * M01) >> 24; }
 
