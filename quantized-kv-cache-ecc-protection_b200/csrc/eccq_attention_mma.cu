@@ -53,23 +53,21 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// corrected nibbles of four codewords; flag bytes (0x80 single, 0xFF double) only when the caller counts errors
 template <int CODEC, bool COUNT>
-__device__ __forceinline__ uint32_t decode_word(uint32_t w, uint32_t& ncorr, uint32_t& ndet) {
-  if (CODEC == ECCQ_CODEC_H84) {
-    const Dec4 d = h84_decode4(w);
-    if (COUNT) { ncorr += __popc(h84_single4(d)); ndet += __popc(h84_double4(d)); }
-    return d.nib;
+__device__ __forceinline__ uint32_t decode_word(uint32_t w, uint32_t& flag) {
+  if (CODEC == ECCQ_CODEC_H84 || CODEC == ECCQ_CODEC_H74) {
+    constexpr int HC = CODEC == ECCQ_CODEC_H74 ? ECCQ_CODEC_H74 : ECCQ_CODEC_H84;
+    const uint32_t sel = hamming_sel4<HC>(w);
+    if (COUNT) flag = prmt(kFlagLutLo, kFlagLutHi, sel);
+    return lop3<kLopXorAnd>(w, prmt(kFlipLutLo, kFlipLutHi, sel), M0F);
   }
-  if (CODEC == ECCQ_CODEC_H74) {
-    const Dec4 d = h74_decode4(w);
-    if (COUNT) ncorr += __popc(d.nz);
-    return d.nib;
-  }
+  flag = 0;
   return w;
 }
 
 template <typename TQ, int CODEC, int D, bool PRECISE, bool COUNT>
-__global__ void __launch_bounds__(kMmaThreads, 3) attn_mma_kernel(CacheGeom g, AttnArgs a, uint64_t* counters) {
+__global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, AttnArgs a, uint64_t* counters) {
   constexpr int KS = D / 16;          // k-steps of QK^T == m-tiles of PV
   constexpr int KW = D / 16;          // 32-bit words of a K row owned by a lane (D/4 bytes)
   constexpr int VW = D / 32;          // words of a V row owned by a lane (D/8 bytes)
@@ -123,7 +121,7 @@ __global__ void __launch_bounds__(kMmaThreads, 3) attn_mma_kernel(CacheGeom g, A
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[mt][e] = 0.0f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};   // heads 2*quad, 2*quad+1
-  uint32_t ncorr = 0, ndet = 0;
+  FlagCount fc;
   const bool do_count = COUNT && pass == 0;
 
   // tiles of this warp: first tile index (in units of 16 tokens) is c0/16 + warp, stride kMmaWarps
@@ -184,12 +182,10 @@ __global__ void __launch_bounds__(kMmaThreads, 3) attn_mma_kernel(CacheGeom g, A
         const bool v0 = do_count && tok0 + grow < c1, v1 = do_count && tok0 + grow + 8 < c1;
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
-          uint32_t cc = 0, dd = 0;
-          const uint32_t n0 = decode_word<CODEC, COUNT>(kr0[s], cc, dd);
-          if (COUNT && v0) { ncorr += cc; ndet += dd; }
-          cc = dd = 0;
-          const uint32_t n1 = decode_word<CODEC, COUNT>(kr1[s], cc, dd);
-          if (COUNT && v1) { ncorr += cc; ndet += dd; }
+          uint32_t f0 = 0, f1 = 0;
+          const uint32_t n0 = decode_word<CODEC, COUNT>(kr0[s], f0);
+          const uint32_t n1 = decode_word<CODEC, COUNT>(kr1[s], f1);
+          if (COUNT) { fc.add(v0 ? f0 : 0u); fc.add(v1 ? f1 : 0u); }
           const uint32_t af[4] = {nib2_to_half2(n0, 0x4140), nib2_to_half2(n1, 0x4140), nib2_to_half2(n0, 0x4342), nib2_to_half2(n1, 0x4342)};
           mma16816(s4, af, qf[s][0], qf[s][1]);
           if (PRECISE) mma16816(s4, af, qf_lo[s][0], qf_lo[s][1]);
@@ -250,9 +246,9 @@ __global__ void __launch_bounds__(kMmaThreads, 3) attn_mma_kernel(CacheGeom g, A
           const bool vok = do_count && tok0 + toks[t] < c1;
 #pragma unroll
           for (int w = 0; w < VW; ++w) {
-            uint32_t cc = 0, dd = 0;
-            vr[t][w] = decode_word<CODEC, COUNT>(vr[t][w], cc, dd);
-            if (COUNT && vok) { ncorr += cc; ndet += dd; }
+            uint32_t f = 0;
+            vr[t][w] = decode_word<CODEC, COUNT>(vr[t][w], f);
+            if (COUNT) fc.add(vok ? f : 0u);
           }
         }
 #pragma unroll
@@ -322,7 +318,7 @@ __global__ void __launch_bounds__(kMmaThreads, 3) attn_mma_kernel(CacheGeom g, A
   }
   if (COUNT) {
     const int idx[2] = {ECCQ_CTR_CORRECTED, ECCQ_CTR_DETECTED};
-    const uint32_t val[2] = {ncorr, ndet};
+    const uint32_t val[2] = {fc.singles(), fc.doubles()};
     block_accumulate<2>(counters, idx, val);
   }
 }

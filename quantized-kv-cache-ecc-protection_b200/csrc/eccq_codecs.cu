@@ -45,30 +45,35 @@ __global__ void __launch_bounds__(kThreads) hamming_encode_kernel(const uint8_t*
 }
 
 // ------------------------------------------------------------------------------------------------ Hamming decode
-// counts accumulate as byte-wide sums inside `ncorr`/`ndet` words (flushed with bytesum() before a byte can overflow)
-template <int CODEC, bool ZERO_DOUBLE>
-__device__ __forceinline__ void dec4(uint32_t x, uint32_t& nib, uint32_t& aux, uint32_t& ncorr, uint32_t& ndet) {
+// hamming_decode4 (eccq_common.cuh) gives corrected nibbles and flag bytes (0x80 single, 0xFF double); the error-type
+// byte of hamming84_triton.py:185-187 (0 none, 1 single, 2 double, 3 parity bit only) additionally needs "syndrome 0 with
+// parity mismatch": one more PRMT look-up G = {clean 0x00, parity-only 0x02, single 0x81, double 0xFF}; its low two bits
+// are the Gray code of the error type.
+template <int CODEC, bool ZERO_DOUBLE, bool AUX>
+__device__ __forceinline__ void dec4(uint32_t x, uint32_t& nib, uint32_t& aux, FlagCount& fc) {
+  constexpr int HC = CODEC == ECCQ_CODEC_H74 ? ECCQ_CODEC_H74 : ECCQ_CODEC_H84;
+  const uint32_t sel = hamming_sel4<HC>(x);
+  const uint32_t flag = prmt(kFlagLutLo, kFlagLutHi, sel);
+  nib = lop3<kLopXorAnd>(x, prmt(kFlipLutLo, kFlipLutHi, sel), M0F);
+  fc.add(flag);
   if (CODEC == ECCQ_CODEC_H84) {
-    const Dec4 d = h84_decode4(x);
-    const uint32_t dbl = h84_double4(d);
-    nib = ZERO_DOUBLE ? (d.nib & ~spread8(dbl)) : d.nib;
-    aux = h84_etype4(d);
-    ncorr += h84_single4(d);
-    ndet += dbl;
-  } else {
-    const Dec4 d = h74_decode4(x);
-    nib = d.nib;
-    aux = d.nz;
-    ncorr += d.nz;
+    if (ZERO_DOUBLE) nib &= ~((flag & M01) * 15u);   // fused_kernels.py:343-344 zeroes double-detected nibbles (Q4)
+    if (AUX) {
+      const uint32_t gcode = prmt(0x81818102u, 0x81818181u, sel) & 0x03030303u;   // 0, 2 (parity only), 1 (single), 3 (double)
+      aux = gcode ^ ((gcode >> 1) & M01);                                           // Gray -> 0, 3, 1, 2
+    }
+  } else if (AUX) {
+    aux = (flag >> 7) & M01;   // hamming74_triton.py:129-160: 1 = syndrome != 0 (corrected)
   }
 }
 
-template <int CODEC, bool ZERO_DOUBLE>
+template <int CODEC, bool ZERO_DOUBLE, bool AUX>
 __global__ void __launch_bounds__(kThreads) hamming_decode_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ nib_out,
                                                                    uint8_t* __restrict__ aux_out, uint64_t* counters,
                                                                    int64_t n, int vec) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  FlagCount fc;
   uint32_t ncorr = 0, ndet = 0;
   int64_t done = 0;
   if (vec) {
@@ -84,28 +89,28 @@ __global__ void __launch_bounds__(kThreads) hamming_decode_kernel(const uint8_t*
       for (int u = 0; u < kUnroll; ++u) {
         const int64_t j = i + (int64_t)u * nthreads;
         if (j < n16) {
-          uint4 o, a;
-          uint32_t ac = 0, ad = 0;
-          dec4<CODEC, ZERO_DOUBLE>(v[u].x, o.x, a.x, ac, ad);
-          dec4<CODEC, ZERO_DOUBLE>(v[u].y, o.y, a.y, ac, ad);
-          dec4<CODEC, ZERO_DOUBLE>(v[u].z, o.z, a.z, ac, ad);
-          dec4<CODEC, ZERO_DOUBLE>(v[u].w, o.w, a.w, ac, ad);
-          ncorr += bytesum(ac);
-          ndet += bytesum(ad);
+          uint4 o, a = make_uint4(0, 0, 0, 0);
+          dec4<CODEC, ZERO_DOUBLE, AUX>(v[u].x, o.x, a.x, fc);
+          dec4<CODEC, ZERO_DOUBLE, AUX>(v[u].y, o.y, a.y, fc);
+          dec4<CODEC, ZERO_DOUBLE, AUX>(v[u].z, o.z, a.z, fc);
+          dec4<CODEC, ZERO_DOUBLE, AUX>(v[u].w, o.w, a.w, fc);
           st_stream(nib_out + (j << 4), o);
-          if (aux_out) st_stream(aux_out + (j << 4), a);
+          if (AUX) st_stream(aux_out + (j << 4), a);
         }
       }
+      // the byte sums of FlagCount stay far below 2^31 over one flush interval
+      ncorr += fc.singles(); ndet += fc.doubles(); fc = FlagCount();
     }
     done = n16 << 4;
   }
   for (int64_t i = done + tid; i < n; i += nthreads) {
-    uint32_t o, a, ac = 0, ad = 0;
-    dec4<CODEC, ZERO_DOUBLE>(in[i], o, a, ac, ad);
-    ncorr += ac & 0xFFu;
-    ndet += ad & 0xFFu;
+    uint32_t o, a = 0;
+    FlagCount f1;
+    dec4<CODEC, ZERO_DOUBLE, AUX>(in[i], o, a, f1);   // upper three bytes are zero codewords: clean
+    ncorr += f1.singles();
+    ndet += f1.doubles();
     nib_out[i] = (uint8_t)o;
-    if (aux_out) aux_out[i] = (uint8_t)a;
+    if (AUX) aux_out[i] = (uint8_t)a;
   }
   const int idx[2] = {ECCQ_CTR_CORRECTED, ECCQ_CTR_DETECTED};
   const uint32_t val[2] = {ncorr, ndet};
@@ -343,6 +348,64 @@ __global__ void __launch_bounds__(kThreads) inject_fast_kernel(const uint8_t* __
   block_accumulate<2>(counters, idx, val);
 }
 
+// Windowed warp-cooperative version (warp_fill_flips, eccq_common.cuh) for the codeword formats of the path: every warp
+// owns windows of kInjWindow x 32 consecutive 16-byte chunks; the chunk loads are issued first, the window's flips are
+// generated into shared memory (one Philox call per eight flips), then masks are applied and stored.  The stream is keyed by
+// (window, lane), so the result does not depend on the grid.  "Affected" elements are counted when a flip lands on an
+// element whose mask was still empty (the atomicOr returns the previous word).
+template <int ES, int NBITS>
+__global__ void __launch_bounds__(kThreads) inject_fast2_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, FastInject fi,
+                                                                 uint64_t* counters, int64_t nchunks) {
+  constexpr int SW = 4;                               // mask words per 16-byte chunk
+  constexpr uint32_t NPOS = (16 / ES) * NBITS;        // candidate bits per chunk
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  __shared__ __align__(16) uint32_t s_flip[(kThreads / 32) * kInjWindow * 32 * SW];
+  for (int i = threadIdx.x; i < (kThreads / 32) * kInjWindow * 32 * SW; i += blockDim.x) s_flip[i] = 0;
+  __syncthreads();
+  uint32_t* smask = s_flip + (threadIdx.x >> 5) * kInjWindow * 32 * SW;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t nwin = (nchunks + kInjWindow * 32 - 1) / (kInjWindow * 32);
+  uint32_t flips = 0, affected = 0;
+  for (int64_t win = warp; win < nwin; win += nwarps) {
+    const int64_t c0 = win * (kInjWindow * 32);
+    const uint32_t nslot = (uint32_t)min((int64_t)kInjWindow * 32, nchunks - c0);
+    uint4 v[kInjWindow];
+#pragma unroll
+    for (int w = 0; w < kInjWindow; ++w)
+      if ((uint32_t)(w * 32 + lane) < nslot) v[w] = ld_stream(in + ((c0 + w * 32 + lane) << 4));
+    GapRng4 rng;
+    rng.init(fi, (uint32_t)win, (uint32_t)(win >> 32) * 32u + (uint32_t)lane);
+    uint32_t first[4];
+    rng.draw(first, true);
+    uint32_t carry = __shfl_sync(FULL, first[0], 0) - 1u;
+    uint32_t hit = 0;
+    flips += warp_fill_flips<NPOS, SW>(rng, carry, smask, nslot * NPOS, lane, [&](uint32_t local, uint32_t& wd, uint32_t& b) {
+      const uint32_t el = local / NBITS;
+      const uint32_t idx = el * (8 * ES) + (local - el * NBITS);   // bit index inside the 128-bit chunk
+      wd = idx >> 5; b = idx & 31u;
+    }, [&](uint32_t old, uint32_t b) {
+      const uint32_t emask = ES == 4 ? 0xFFFFFFFFu : 0xFFu << (b & 24u);
+      hit += (old & emask) == 0u;
+    });
+    affected += hit;
+#pragma unroll
+    for (int w = 0; w < kInjWindow; ++w) {
+      if ((uint32_t)(w * 32 + lane) < nslot) {
+        uint4* slot = reinterpret_cast<uint4*>(smask + (w * 32 + lane) * SW);
+        const uint4 m = *slot;
+        *slot = make_uint4(0, 0, 0, 0);
+        st_stream(out + ((c0 + w * 32 + lane) << 4), make_uint4(v[w].x ^ m.x, v[w].y ^ m.y, v[w].z ^ m.z, v[w].w ^ m.w));
+      }
+    }
+    __syncwarp();
+  }
+  const int idx[2] = {ECCQ_CTR_FLIPPED, ECCQ_CTR_AFFECTED};
+  const uint32_t val[2] = {flips, affected};
+  block_accumulate<2>(counters, idx, val);
+}
+
 // ------------------------------------------------------------------------------------------------ interpolation
 // [outer, len, inner] view; neighbours at +-inner. VEC: inner % 16 == 0 and 16-byte aligned bases.
 template <bool VEC>
@@ -435,8 +498,9 @@ extern "C" int eccq_h74_decode(const uint8_t* cw, uint8_t* nib, uint8_t* flag, u
   if (n < 0 || (n && (!cw || !nib))) return fail(ECCQ_EINVAL, "h74_decode: bad arguments");
   if (n == 0) return ECCQ_OK;
   const int vec = aligned16(cw) && aligned16(nib) && (!flag || aligned16(flag));
-  hamming_decode_kernel<ECCQ_CODEC_H74, false><<<grid_for(n, kThreads * 16 * kUnroll), kThreads, 0, (cudaStream_t)stream>>>(
-      cw, nib, flag, counters, n, vec);
+  const int grid = grid_for(n, kThreads * 16 * kUnroll);
+  if (flag) hamming_decode_kernel<ECCQ_CODEC_H74, false, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(cw, nib, flag, counters, n, vec);
+  else hamming_decode_kernel<ECCQ_CODEC_H74, false, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(cw, nib, flag, counters, n, vec);
   return check_launch("h74_decode");
 }
 
@@ -446,10 +510,14 @@ extern "C" int eccq_h84_decode(const uint8_t* cw, uint8_t* nib, uint8_t* etype, 
   if (n == 0) return ECCQ_OK;
   const int vec = aligned16(cw) && aligned16(nib) && (!etype || aligned16(etype));
   const int grid = grid_for(n, kThreads * 16 * kUnroll);
-  if (zero_double)
-    hamming_decode_kernel<ECCQ_CODEC_H84, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(cw, nib, etype, counters, n, vec);
-  else
-    hamming_decode_kernel<ECCQ_CODEC_H84, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(cw, nib, etype, counters, n, vec);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zero_double) {
+    if (etype) hamming_decode_kernel<ECCQ_CODEC_H84, true, true><<<grid, kThreads, 0, st>>>(cw, nib, etype, counters, n, vec);
+    else hamming_decode_kernel<ECCQ_CODEC_H84, true, false><<<grid, kThreads, 0, st>>>(cw, nib, etype, counters, n, vec);
+  } else {
+    if (etype) hamming_decode_kernel<ECCQ_CODEC_H84, false, true><<<grid, kThreads, 0, st>>>(cw, nib, etype, counters, n, vec);
+    else hamming_decode_kernel<ECCQ_CODEC_H84, false, false><<<grid, kThreads, 0, st>>>(cw, nib, etype, counters, n, vec);
+  }
   return check_launch("h84_decode");
 }
 
@@ -513,6 +581,20 @@ extern "C" int eccq_inject_philox_fast(const void* in, void* out, int elem_size,
   const FastInject fi = make_fast_inject(ber, seed);
   const int64_t nbytes = n * elem_size;
   const int vec = aligned16(in) && aligned16(out);
+  if (vec && nbytes % 16 == 0 && !(ber >= 1.0f)) {   // the codeword formats of the path: windowed warp-cooperative kernel
+    const int64_t nchunks = nbytes >> 4;
+    const int grid = grid_for(nchunks, (kThreads / 32) * kInjWindow * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint8_t* ip = (const uint8_t*)in;
+    uint8_t* op = (uint8_t*)out;
+    bool done = true;
+    if (elem_size == 1 && n_bits == 8) inject_fast2_kernel<1, 8><<<grid, kThreads, 0, st>>>(ip, op, fi, counters, nchunks);
+    else if (elem_size == 1 && n_bits == 7) inject_fast2_kernel<1, 7><<<grid, kThreads, 0, st>>>(ip, op, fi, counters, nchunks);
+    else if (elem_size == 1 && n_bits == 4) inject_fast2_kernel<1, 4><<<grid, kThreads, 0, st>>>(ip, op, fi, counters, nchunks);
+    else if (elem_size == 4 && n_bits == 24) inject_fast2_kernel<4, 24><<<grid, kThreads, 0, st>>>(ip, op, fi, counters, nchunks);
+    else done = false;
+    if (done) return check_launch("inject_philox_fast");
+  }
   inject_fast_kernel<<<grid_for(nbytes, kThreads * 16), kThreads, 0, (cudaStream_t)stream>>>(
       (const uint8_t*)in, (uint8_t*)out, elem_size, n_bits, fi, counters, nbytes, vec);
   return check_launch("inject_philox_fast");

@@ -330,6 +330,87 @@ __device__ __forceinline__ void fast_flip_positions(const FastInject& fi, uint64
   }
 }
 
+// ------------------------------------------------------------------------------------------------ own-stream injection, windowed
+// One Bernoulli(p) process runs over the warp's bit stream of a WINDOW of up to kInjWindow warp-iterations: slot s (= iteration
+// * 32 + lane) owns NPOS consecutive candidate positions.  Every round each lane draws FOUR geometric gaps from one
+// Philox-4x32-10 call, a warp prefix sum turns the 128 gaps into 128 flip positions, and each position inside the window is
+// OR-ed into its slot's mask in shared memory (SW words per slot, zero on entry).  The first position past the window is
+// carried into the next window (later draws are discarded: the process is memoryless).  At BER 1e-2 a 4-iteration window
+// of Hamming(8,4) rows holds ~330 flips = 3 rounds; the cost per value is a quarter of the per-iteration scheme's.
+constexpr int kInjWindow = 4;
+struct GapRng4 {
+  uint32_t ctr, c0, c1, k0, k1;
+  uint32_t spare0, spare1;   // upper halves of the last Philox call (every call feeds two rounds)
+  float inv;
+  __device__ __forceinline__ void init(const FastInject& fi, uint32_t a, uint32_t b) {
+    ctr = 0; c0 = a; c1 = b; k0 = fi.seed_lo; k1 = fi.seed_hi; inv = fi.inv_lg2_q;
+  }
+  // gap = floor(log2(u) / log2(1-p)) >= 0 with u = (h+1)/65536 in (0,1] from 16 random bits (h placed on mantissa bits
+  // 7..22: 2 - [1,2) = (65536 - h)/65536), saturated at 2^24; increments returned are 1 + gap.  16-bit uniforms bias the
+  // flip rate by < 0.05 % (the tail beyond log(2^-16)/log(1-p) gaps is truncated), far inside the statistical tolerance the
+  // injector is held to, and halve the Philox work per flip.
+  __device__ __forceinline__ uint32_t inc(uint32_t mant) const {
+    const float u = 2.0f - __uint_as_float(0x3F800000u | mant);
+    return 1u + (uint32_t)fminf(__log2f(u) * inv, 16777216.0f);
+  }
+  // `fresh` must be warp-uniform: true -> new Philox call, false -> the spare halves of the previous one
+  __device__ __forceinline__ void draw(uint32_t (&i)[4], bool fresh) {
+    if (fresh) {
+      const uint4 r = philox4x32_10(make_uint4(c0, c1, ctr++, 0x45434351u), make_uint2(k0, k1));
+      i[0] = inc((r.x & 0xFFFFu) << 7); i[1] = inc((r.y & 0xFFFFu) << 7);
+      i[2] = inc((r.z & 0xFFFFu) << 7); i[3] = inc((r.w & 0xFFFFu) << 7);
+      spare0 = __byte_perm(r.x, r.y, 0x7632);   // {hi16(r.y), hi16(r.x)}
+      spare1 = __byte_perm(r.z, r.w, 0x7632);
+    } else {
+      i[0] = inc((spare0 & 0xFFFFu) << 7); i[1] = inc((spare0 >> 16) << 7);
+      i[2] = inc((spare1 & 0xFFFFu) << 7); i[3] = inc((spare1 >> 16) << 7);
+    }
+  }
+};
+// W = window length in candidate positions (< 2^20); carry = distance from the window start to the next flip (warp-uniform).
+// Returns the number of flips this lane placed.
+struct NoPlaceHook { __device__ __forceinline__ void operator()(uint32_t, uint32_t) const {} };
+// on_place(old_word, bit) is called for every flip placed (old_word = the mask word before the OR)
+template <uint32_t NPOS, int SW, class Place, class Hook = NoPlaceHook>
+__device__ __forceinline__ uint32_t warp_fill_flips(GapRng4& rng, uint32_t& carry, uint32_t* smask, uint32_t W, int lane, Place place,
+                                                    Hook on_place = Hook()) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  if (carry >= W) { carry -= W; return 0; }
+  uint32_t base = carry, placed = 0;
+  for (bool fresh = true;; fresh = !fresh) {   // every window starts on a fresh call: unused spares are simply dropped
+    uint32_t inc[4];
+    rng.draw(inc, fresh);
+    const uint32_t mine = inc[0] + inc[1] + inc[2] + inc[3];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    uint32_t f = base + incl - mine;   // position of this lane's first flip of the round
+    uint32_t cand = 0xFFFFFFFFu;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (f < W) {
+        const uint32_t slot = f / NPOS;
+        uint32_t w, b;
+        place(f - slot * NPOS, w, b);
+        on_place(atomicOr(&smask[slot * SW + w], 1u << b), b);
+        ++placed;
+      } else {
+        cand = min(cand, f);
+      }
+      f += inc[q];
+    }
+    const uint32_t fb = min(__reduce_min_sync(FULL, cand), base + total);
+    if (fb >= W) { carry = fb - W; break; }
+    base = fb;
+  }
+  __syncwarp();
+  return placed;
+}
+
 // ------------------------------------------------------------------------------------------------ float <-> INT4
 template <typename T> struct Cvt;
 template <> struct Cvt<float> {
