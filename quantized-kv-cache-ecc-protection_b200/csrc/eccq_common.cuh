@@ -24,6 +24,15 @@ __device__ __forceinline__ void st_stream8(void* p, uint2 v) { __stcs(reinterpre
 
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// cp.async: 16-byte global -> shared copies that bypass the register file (page staging)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
 // One atomicAdd per CTA per counter: lanes -> warp (redux) -> shared -> global.
 template <int NV>
 __device__ __forceinline__ void block_accumulate(uint64_t* counters, const int (&idx)[NV], const uint32_t (&val)[NV]) {
