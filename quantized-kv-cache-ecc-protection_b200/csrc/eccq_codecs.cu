@@ -581,7 +581,7 @@ extern "C" int eccq_inject_philox_fast(const void* in, void* out, int elem_size,
   const FastInject fi = make_fast_inject(ber, seed);
   const int64_t nbytes = n * elem_size;
   const int vec = aligned16(in) && aligned16(out);
-  if (vec && nbytes % 16 == 0 && !(ber >= 1.0f)) {   // the codeword formats of the path: windowed warp-cooperative kernel
+  if (vec && nbytes >= 16 && !(ber >= 1.0f)) {   // the codeword formats of the path: windowed warp-cooperative kernel
     const int64_t nchunks = nbytes >> 4;
     const int grid = grid_for(nchunks, (kThreads / 32) * kInjWindow * 32);
     cudaStream_t st = (cudaStream_t)stream;
@@ -593,7 +593,14 @@ extern "C" int eccq_inject_philox_fast(const void* in, void* out, int elem_size,
     else if (elem_size == 1 && n_bits == 4) inject_fast2_kernel<1, 4><<<grid, kThreads, 0, st>>>(ip, op, fi, counters, nchunks);
     else if (elem_size == 4 && n_bits == 24) inject_fast2_kernel<4, 24><<<grid, kThreads, 0, st>>>(ip, op, fi, counters, nchunks);
     else done = false;
-    if (done) return check_launch("inject_philox_fast");
+    if (done) {
+      const int64_t tail = nbytes - (nchunks << 4);   // < 16 bytes: the per-chunk kernel on its own stream
+      if (tail > 0) {
+        const FastInject ft = make_fast_inject(ber, seed ^ 0x5BD1E9955BD1E995ull);
+        inject_fast_kernel<<<1, 32, 0, st>>>(ip + (nchunks << 4), op + (nchunks << 4), elem_size, n_bits, ft, counters, tail, 0);
+      }
+      return check_launch("inject_philox_fast");
+    }
   }
   inject_fast_kernel<<<grid_for(nbytes, kThreads * 16), kThreads, 0, (cudaStream_t)stream>>>(
       (const uint8_t*)in, (uint8_t*)out, elem_size, n_bits, fi, counters, nbytes, vec);

@@ -24,7 +24,11 @@ if has list; then
     python bench.py --steps 5 --warmup 3 --no-cpu > $O/ncu_list.log 2>&1; echo "ncu list exit $?"
 fi
 if has full; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'cache_write|cache_read|attn_' -s 6 -c 8 \
-    -f -o $O/full python bench.py --steps 3 --warmup 3 --no-cpu > $O/ncu_full.log 2>&1; echo "ncu full exit $?"
-  ls -la $O
+  # one ncu --set full capture of the bench's hot kernels; reduced on the box (the .ncu-rep embeds the 12 MB module)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'cache_write|cache_read|attn_mma' -s 6 -c 6 \
+    -f -o /tmp/full python bench.py --steps 3 --warmup 3 --no-cpu > $O/ncu_full.log 2>&1; echo "ncu full exit $?"
+  python tools/ncu_summary.py /tmp/full.ncu-rep > $O/ncu_full_summary.txt 2>&1
+  ncu -i /tmp/full.ncu-rep --page raw --csv > $O/ncu_full_raw.csv 2>/dev/null
+  rm -f /tmp/full.ncu-rep
+  cat $O/ncu_full_summary.txt
 fi
