@@ -1,9 +1,9 @@
 // eccq_cache_read2.cuh -- fused cache read, second generation (included by eccq_cache.cu; uses CacheGeom / ReadArgs).
 //
 // One warp per (tensor, sequence, head, block) page as in cache_read_kernel -- every lane keeps SPL consecutive token slots
-// of its 16-byte column in registers -- but each warp STREAMS through a contiguous range of pages of the flattened
-// (sequence, head, tensor, block) order, so that
-//   * the range is split evenly over the resident warps (no tail wave, no per-page index divisions);
+// of its 16-byte column in registers -- but each warp STREAMS through a chunk of consecutive pages of one
+// (sequence, tensor, head) run, so that
+//   * the work is split evenly over the resident warps (no tail wave, no per-page index divisions);
 //   * the next page's codewords and scales are loaded while the current page is decoded (2 pages in flight per warp);
 //   * the temporal neighbours across page edges are already on chip: the previous page's last row is carried in
 //     registers, the next page's first row is the prefetched one (shuffled from lane group 0 and decoded under a vote).
@@ -92,8 +92,11 @@ __device__ __forceinline__ void load_scales(const float* p, float (&sc)[SPL]) {
 }
 
 
+// INTERP = true: the next page is prefetched into registers (it is also the right neighbour of this page's last row);
+// 2 CTAs per SM.  INTERP = false: less arithmetic per byte, so the smoother memory traffic of 3 CTAs per SM (<= 85
+// registers, pages loaded at the top of their own iteration) wins over the deeper per-warp prefetch.
 template <typename TO, int CODEC, bool INTERP, int C, int SPL>
-__global__ void __launch_bounds__(256, 2) cache_read2_kernel(CacheGeom g, ReadArgs a, int nblk_logical, int chunk, int head_fastest,
+__global__ void __launch_bounds__(256, (INTERP && CODEC == ECCQ_CODEC_H84) ? 2 : 3) cache_read2_kernel(CacheGeom g, ReadArgs a, int nblk_logical, int chunk, int head_fastest,
                                                               uint64_t* counters) {
   constexpr int D = 16 * C, GROUPS = 32 / C, BS = GROUPS * SPL;
   constexpr bool kHamming = CODEC == ECCQ_CODEC_H84 || CODEC == ECCQ_CODEC_H74;
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(256, 2) cache_read2_kernel(CacheGeom g, ReadAr
     float sc[SPL];
 #pragma unroll
     for (int s = 0; s < SPL; ++s) raw[s] = make_uint4(0, 0, 0, 0);
-    if (blk >= 0) {
+    if (kInterp && blk >= 0) {
       const int64_t page = (int64_t)blk * LH + lh;
 #pragma unroll
       for (int s = 0; s < SPL; ++s) raw[s] = ld_stream(cache + page * page_bytes + (slot0 + s) * D);
@@ -173,11 +176,18 @@ __global__ void __launch_bounds__(256, 2) cache_read2_kernel(CacheGeom g, ReadAr
       float scn[SPL];
 #pragma unroll
       for (int s = 0; s < SPL; ++s) { rawn[s] = make_uint4(0, 0, 0, 0); scn[s] = 0.0f; }
-      if (blk_n >= 0) {
-        const int64_t page = (int64_t)blk_n * LH + lh;
+      if (kInterp) {
+        if (blk_n >= 0) {
+          const int64_t page = (int64_t)blk_n * LH + lh;
 #pragma unroll
-        for (int s = 0; s < SPL; ++s) rawn[s] = ld_stream(cache + page * page_bytes + (slot0 + s) * D);
-        load_scales<SPL>(scales + page * BS + slot0, scn);
+          for (int s = 0; s < SPL; ++s) rawn[s] = ld_stream(cache + page * page_bytes + (slot0 + s) * D);
+          load_scales<SPL>(scales + page * BS + slot0, scn);
+        }
+      } else if (blk >= 0) {   // no prefetch: this page's loads
+        const int64_t page = (int64_t)blk * LH + lh;
+#pragma unroll
+        for (int s = 0; s < SPL; ++s) raw[s] = ld_stream(cache + page * page_bytes + (slot0 + s) * D);
+        load_scales<SPL>(scales + page * BS + slot0, sc);
       }
       const int blk_nn = j + 2 < nb_ctx ? bt[j + 2] : -1;
       const int t0 = j * BS;
@@ -292,8 +302,10 @@ __global__ void __launch_bounds__(256, 2) cache_read2_kernel(CacheGeom g, ReadAr
         for (int k = 0; k < 4; ++k) carry[k] = 0;
       }
       // ---- rotate
+      if (kInterp) {
 #pragma unroll
-      for (int s = 0; s < SPL; ++s) { raw[s] = rawn[s]; sc[s] = scn[s]; }
+        for (int s = 0; s < SPL; ++s) { raw[s] = rawn[s]; sc[s] = scn[s]; }
+      }
       blk = blk_n;
       blk_n = blk_nn;
       obase += (int64_t)BS * ostride;
