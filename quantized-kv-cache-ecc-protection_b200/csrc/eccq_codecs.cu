@@ -381,10 +381,11 @@ __global__ void __launch_bounds__(kThreads) inject_fast2_kernel(const uint8_t* _
     rng.draw(first, true);
     uint32_t carry = __shfl_sync(FULL, first[0], 0) - 1u;
     uint32_t hit = 0;
-    flips += warp_fill_flips<NPOS, SW>(rng, carry, smask, nslot * NPOS, lane, [&](uint32_t local, uint32_t& wd, uint32_t& b) {
+    flips += warp_fill_flips<NPOS, SW>(rng, carry, smask, nslot * NPOS, lane, [&](uint32_t, uint32_t local, uint32_t& wd, uint32_t& b) {
       const uint32_t el = local / NBITS;
       const uint32_t idx = el * (8 * ES) + (local - el * NBITS);   // bit index inside the 128-bit chunk
       wd = idx >> 5; b = idx & 31u;
+      return true;
     }, [&](uint32_t old, uint32_t b) {
       const uint32_t emask = ES == 4 ? 0xFFFFFFFFu : 0xFFu << (b & 24u);
       hit += (old & emask) == 0u;

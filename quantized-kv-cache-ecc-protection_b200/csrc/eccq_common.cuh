@@ -377,6 +377,7 @@ struct GapRng4 {
   }
 };
 // W = window length in candidate positions (< 2^20); carry = distance from the window start to the next flip (warp-uniform).
+// place(slot, local, word, bit) maps a position to its mask word / bit and returns whether the position exists.
 // Returns the number of flips this lane placed.
 struct NoPlaceHook { __device__ __forceinline__ void operator()(uint32_t, uint32_t) const {} };
 // on_place(old_word, bit) is called for every flip placed (old_word = the mask word before the OR)
@@ -404,9 +405,10 @@ __device__ __forceinline__ uint32_t warp_fill_flips(GapRng4& rng, uint32_t& carr
       if (f < W) {
         const uint32_t slot = f / NPOS;
         uint32_t w, b;
-        place(f - slot * NPOS, w, b);
-        on_place(atomicOr(&smask[slot * SW + w], 1u << b), b);
-        ++placed;
+        if (place(slot, f - slot * NPOS, w, b)) {   // false: the position does not exist (padding of a ragged layout)
+          on_place(atomicOr(&smask[slot * SW + w], 1u << b), b);
+          ++placed;
+        }
       } else {
         cand = min(cand, f);
       }

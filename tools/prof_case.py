@@ -66,7 +66,7 @@ elif case in ("h84enc", "h84dec"):
         timed(lambda: lib.eccq_h84_decode(P(cw), P(o1), P(o2), P(ctr), N, 0, SP), 3 * N)
 elif case.startswith(("write", "read")):
     B, S = 16, 8192
-    codec = "golay" if case.endswith("g") else "int4" if "int4" in case else "hamming84"
+    codec = "golay" if "g" in case else "int4" if "int4" in case else "hamming84"
     nblk = B * S // BS
     k = torch.randn(B, S, H * D, device=dev, dtype=torch.float16)
     v = torch.randn(B, S, H * D, device=dev, dtype=torch.float16)
