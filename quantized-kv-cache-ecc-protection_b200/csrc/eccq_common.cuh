@@ -354,31 +354,31 @@ struct GapRng4 {
   __device__ __forceinline__ void init(const FastInject& fi, uint32_t a, uint32_t b) {
     ctr = 0; c0 = a; c1 = b; k0 = fi.seed_lo; k1 = fi.seed_hi; inv = fi.inv_lg2_q;
   }
-  // gap = floor(log2(u) / log2(1-p)) >= 0 with u = (h+1)/65536 in (0,1] from 16 random bits (h placed on mantissa bits
-  // 7..22: 2 - [1,2) = (65536 - h)/65536), saturated at 2^24; increments returned are 1 + gap.  16-bit uniforms bias the
-  // flip rate by < 0.05 % (the tail beyond log(2^-16)/log(1-p) gaps is truncated), far inside the statistical tolerance the
-  // injector is held to, and halve the Philox work per flip.
-  __device__ __forceinline__ uint32_t inc(uint32_t mant) const {
-    const float u = 2.0f - __uint_as_float(0x3F800000u | mant);
-    return 1u + (uint32_t)fminf(__log2f(u) * inv, 16777216.0f);
+  // gap = floor(log2(u) / log2(1-p)) >= 0 with u = 1 - h/65536 in (0,1] from 16 random bits h, saturated at 2^24;
+  // increments returned are 1 + gap.  `m` is the float 2^23 + h (PRMT puts the 16 bits under the exponent byte 0x4B), so
+  // u is ONE FFMA: (2^23 + h) * -2^-16 + 129.  16-bit uniforms bias the flip rate by < 0.05 % (the tail beyond
+  // log(2^-16)/log(1-p) gaps is truncated), far inside the statistical tolerance the injector is held to, and halve the
+  // Philox work per flip.
+  __device__ __forceinline__ uint32_t inc(uint32_t m) const {
+    const float u = fmaf(__uint_as_float(m), -1.52587890625e-5f, 129.0f);
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));   // u >= 2^-16: never denormal
+    return 1u + (uint32_t)fminf(lg * inv, 16777216.0f);
   }
+  static __device__ __forceinline__ uint32_t lo16(uint32_t r) { return __byte_perm(r, 0x4B000000u, 0x7610); }
+  static __device__ __forceinline__ uint32_t hi16(uint32_t r) { return __byte_perm(r, 0x4B000000u, 0x7632); }
   // `fresh` must be warp-uniform: true -> new Philox call, false -> the spare halves of the previous one
   __device__ __forceinline__ void draw(uint32_t (&i)[4], bool fresh) {
     if (fresh) {
       const uint4 r = philox4x32_10(make_uint4(c0, c1, ctr++, 0x45434351u), make_uint2(k0, k1));
-      i[0] = inc((r.x & 0xFFFFu) << 7); i[1] = inc((r.y & 0xFFFFu) << 7);
-      i[2] = inc((r.z & 0xFFFFu) << 7); i[3] = inc((r.w & 0xFFFFu) << 7);
+      i[0] = inc(lo16(r.x)); i[1] = inc(lo16(r.y)); i[2] = inc(lo16(r.z)); i[3] = inc(lo16(r.w));
       spare0 = __byte_perm(r.x, r.y, 0x7632);   // {hi16(r.y), hi16(r.x)}
       spare1 = __byte_perm(r.z, r.w, 0x7632);
     } else {
-      i[0] = inc((spare0 & 0xFFFFu) << 7); i[1] = inc((spare0 >> 16) << 7);
-      i[2] = inc((spare1 & 0xFFFFu) << 7); i[3] = inc((spare1 >> 16) << 7);
+      i[0] = inc(lo16(spare0)); i[1] = inc(hi16(spare0)); i[2] = inc(lo16(spare1)); i[3] = inc(hi16(spare1));
     }
   }
 };
-// W = window length in candidate positions (< 2^20); carry = distance from the window start to the next flip (warp-uniform).
-// place(slot, local, word, bit) maps a position to its mask word / bit and returns whether the position exists.
-// Returns the number of flips this lane placed.
 struct NoPlaceHook { __device__ __forceinline__ void operator()(uint32_t, uint32_t) const {} };
 // on_place(old_word, bit) is called for every flip placed (old_word = the mask word before the OR)
 template <uint32_t NPOS, int SW, class Place, class Hook = NoPlaceHook>
@@ -403,11 +403,16 @@ __device__ __forceinline__ uint32_t warp_fill_flips(GapRng4& rng, uint32_t& carr
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (f < W) {
-        const uint32_t slot = f / NPOS;
-        uint32_t w, b;
-        if (place(slot, f - slot * NPOS, w, b)) {   // false: the position does not exist (padding of a ragged layout)
-          on_place(atomicOr(&smask[slot * SW + w], 1u << b), b);
+        if constexpr (NPOS == SW * 32u) {   // dense layout: the window's bit index IS the mask bit index
+          on_place(atomicOr(&smask[f >> 5], 1u << (f & 31u)), f & 31u);
           ++placed;
+        } else {
+          const uint32_t slot = f / NPOS;
+          uint32_t w, b;
+          if (place(slot, f - slot * NPOS, w, b)) {   // false: the position does not exist (padding of a ragged layout)
+            on_place(atomicOr(&smask[slot * SW + w], 1u << b), b);
+            ++placed;
+          }
         }
       } else {
         cand = min(cand, f);

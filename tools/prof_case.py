@@ -22,7 +22,8 @@ lib = _lib.load()
 P = _lib.ptr
 SP = _lib.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 ctr = _lib.new_counters(dev)
-H, D, BS = 8, 128, 16
+import os
+H, D, BS = int(os.environ.get("PC_H", 8)), int(os.environ.get("PC_D", 128)), int(os.environ.get("PC_BS", 16))
 torch.manual_seed(0)
 
 
