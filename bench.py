@@ -318,6 +318,16 @@ def run_ours(args):
         except Exception as exc:  # never lose the headline line to the secondary metric
             attn = {"error": repr(exc)}
 
+    # ---------------- secondary metric: C4 shape (Mistral-7B KV, Golay(24,12), batch 8 x 32768, kv-heads sharded over ranks)
+    golay = None
+    if not args.no_attention:
+        try:
+            del k, v, k_out, v_out, images, kh, vh
+            torch.cuda.empty_cache()
+            golay = bench_golay_c4(torch, dev, lib, _lib, SimpleBlockManager, world)
+        except Exception as exc:
+            golay = {"error": repr(exc)}
+
     if rank == 0:
         cb = cpu_leg(3, 1, min_seconds=10.0) if not args.no_cpu else None   # ~10 s of host work
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
@@ -331,7 +341,7 @@ def run_ours(args):
                 "roofline": roofline, "kernels": kern, "write_kernel_ber_sweep": ber_sweep, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": 2 * K,
                 "clocks": sampler.report(),
                 "counters": {"corrected": stats[0], "detected": stats[1], "bits_flipped": stats[2], "interpolated": stats[5]},
-                "decode_attention": attn}
+                "decode_attention": attn, "golay_c4": golay}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
@@ -377,6 +387,51 @@ def bench_attention(torch, dev, lib, _lib, paged_attention_ecc, SimpleBlockManag
             "context_tokens_per_s_all_gpus": world * Bq * ctx / (ms * 1e-3),
             "generated_tokens_per_s_32_layers": world * Bq / (32 * ms * 1e-3), "gbs": nbytes / (ms * 1e-3) / 1e9,
             "roofline_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "kernel": "attn_mma_kernel (ECC decode in the K/V prologue, mma.sync m16n8k16) + attn_merge_kernel"}
+
+
+def bench_golay_c4(torch, dev, lib, _lib, SimpleBlockManager, world):
+    """C4: batch 8 x seq 32768, 8 kv-heads x 128, Golay(24,12) per-row packing (43 codewords per row); the kv-heads are
+    sharded over the ranks (8/world heads each).  Fused write with on-device injection at BER 1e-2, then fused read."""
+    Bg, Sg = 8, 32768
+    Hl = max(1, HKV // world)
+    nblk_seq = Sg // BS
+    nblk = Bg * nblk_seq
+    m = SimpleBlockManager(nblk, BS, 1, Hl, D, device=dev, codec="golay")
+    m.block_table = torch.randperm(nblk, generator=torch.Generator().manual_seed(11)).to(torch.int32).view(Bg, nblk_seq).to(dev)
+    kk = torch.randn(Bg, Sg, Hl * D, device=dev, dtype=torch.float16)
+    vv = torch.randn(Bg, Sg, Hl * D, device=dev, dtype=torch.float16)
+    ko = torch.empty(Bg, Sg, Hl, D, device=dev, dtype=torch.float16)
+    vo = torch.empty_like(ko)
+    cl = torch.full((Bg,), Sg, dtype=torch.int32, device=dev)
+    P = _lib.ptr
+    sp = _lib.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    desc = m.desc()
+    vals = 2 * Bg * Sg * Hl * D
+    cwb = 4 * ((D + 2) // 3) / D
+
+    def w():
+        _lib.check(lib.eccq_cache_write(desc, P(kk), P(vv), _lib.ECCQ_F16, P(m.block_table), nblk_seq, None, Bg, Sg, 0, _lib.INJECT_PHILOX_FAST,
+                                        None, None, BER, SEED, 0, None, sp), "cache_write")
+
+    def r():
+        _lib.check(lib.eccq_cache_read(desc, P(m.block_table), nblk_seq, P(cl), Bg, Sg, 0, 0, _lib.ECCQ_F16, P(ko), P(vo), None, None, None, sp),
+                   "cache_read")
+
+    out = {"workload": f"C4: batch 8 x 32768, {Hl} of 8 kv-heads per rank, D 128, Golay(24,12), BER 1e-2, one layer"}
+    peak, _ = hbm_peak()
+    for name, fn, nbytes in (("write", w, vals * (2 + cwb + 4 / D)), ("read", r, vals * (cwb + 4 / D + 2))):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 5
+        out[name] = {"ms": ms, "gbs_per_gpu": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+                     "codewords_per_s_all_gpus": world * vals / D * ((D + 2) // 3) / (ms * 1e-3)}
+    return out
 
 
 def main():
