@@ -304,10 +304,11 @@ static int dispatch_attn(const CacheGeom& g, const AttnArgs& a, uint64_t* counte
 }
 
 template <typename TQ>
-static int try_attn_mma(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st);  // eccq_attention_mma.cu
+static int try_attn_mma(const CacheGeom& g, AttnArgs& a, uint64_t* counters, cudaStream_t st);  // eccq_attention_mma.cu (may coarsen a.chunk / a.nsplit)
 
 template <typename TQ>
-static int run_attn(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+static int run_attn(const CacheGeom& g, const AttnArgs& a_in, uint64_t* counters, cudaStream_t st) {
+  AttnArgs a = a_in;
   int rc;
   if (!a.force_general && try_attn_mma<TQ>(g, a, counters, st)) {
     dim3 mg0(a.Hq, a.nseq);

@@ -58,32 +58,87 @@ __device__ __forceinline__ uint32_t decode_word(uint32_t w, uint32_t& flag) {
   return w;
 }
 
-template <typename TQ, int CODEC, int D, bool PRECISE, bool COUNT>
-__global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, AttnArgs a, uint64_t* counters) {
+// LUT = true: the "table" variant.  The decode prologue of the SWAR variant keeps the ALU pipe 71 % busy (10 ALU operations
+// per four codewords + 2 for the fp16 expansion) while HBM idles at 40 %.  Here a 256-entry table in shared memory maps a
+// codeword byte straight to its corrected value as an fp16 operand: the entry is the half 0xHB00 = fp16(n - 8) (the low byte
+// of fp16(n - 8) is zero for every integer in [-8, 7]).  The table is replicated per bank -- entry c of lane L lives at byte
+// c*256 + L*4 -- so every look-up is conflict-free, and the address is ONE PRMT ({0, 0, codeword byte, lane*4}).  Two
+// look-ups are merged into a half2 operand with one IMAD (FMA-heavy pipe).  Per value: 1 ALU operation + 1 LDS instead of
+// 3.6 ALU operations.  (A 65 536-entry pair table was tried first: 5.4 bank-conflict wavefronts per look-up made it
+// shared-memory bound and slower than SWAR.)  The table takes 64 KB, so the kernel is persistent: one 8-warp CTA per SM
+// builds it once and loops over (sequence, kv-head, chunk) items.  Used when errors are not counted (the counters need the
+// flag bytes of the SWAR decode).
+constexpr int kLutWarps = 16;
+constexpr int kLutLowWarps = 6;        // warps whose staging lies below the table (6 x 9.25 KB < 63 KB)
+constexpr int kLutTableBytes = 65536;
+
+// dynamic shared memory of attn_mma_kernel; the table variant keeps its look-up table at the start of it
+extern __shared__ __align__(16) unsigned char eccq_attn_smem[];
+
+// The table sits at the ABSOLUTE shared-window address 0x10000 (64 KB aligned), so the complete address of a look-up --
+// 0x10000 + byte K of x * 256 + lane * 4 -- is composed by ONE PRMT from x and the register `lane4t` = 0x00010000 | lane*4;
+// no add.  The staging areas of the warps are placed around it (see the kernel prologue).
+constexpr uint32_t kLutTableAddr = 0x10000u;
+template <int K>
+__device__ __forceinline__ uint32_t lut_byte(uint32_t, uint32_t x, uint32_t lane4t) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(prmt(x, lane4t, 0x7604u | (K << 4))));
+  return v;
+}
+__device__ __forceinline__ uint32_t half_pair(uint32_t lo, uint32_t hi) { return hi * 65536u + lo; }
+
+template <typename TQ, int CODEC, int D, bool PRECISE, bool COUNT, int LUT>
+__global__ void __launch_bounds__(LUT ? kLutWarps * 32 : kMmaThreads, LUT ? 1 : 4) attn_mma_kernel(CacheGeom g, AttnArgs a, uint64_t* counters,
+                                                                                                  const uint16_t* pair_tab) {
+  constexpr int NW = LUT ? kLutWarps : kMmaWarps;   // warps per CTA
+  constexpr bool LUT_K = LUT == 1 || LUT == 3, LUT_V = LUT == 1 || LUT == 2;   // which operand uses the table
   constexpr int KS = D / 16;          // k-steps of QK^T == m-tiles of PV
   constexpr int KW = D / 16;          // 32-bit words of a K row owned by a lane (D/4 bytes)
   constexpr int VW = D / 32;          // words of a V row owned by a lane (D/8 bytes)
   constexpr int ROW = D + 16;         // padded smem row stride: conflict-free 16-byte reads
   constexpr int STAGE = 2 * kTile * ROW + 2 * kTile * 4;   // K rows, V rows, k scales, v scales
-  extern __shared__ __align__(16) unsigned char smem[];
-
-  const int split = blockIdx.x;
+  static_assert(!(LUT && COUNT), "the table variant does not produce error flags");
+  // Shared-memory layout of the table variant (absolute shared-window addresses; `base` = start of the dynamic window):
+  //   [base, 0x10000)            staging of warps 0 .. kLutLowWarps-1
+  //   [0x10000, 0x20000)         the look-up table
+  //   [0x20000, ...)             staging of the remaining warps; reused as the merge area at the end of an item
+  unsigned char* const smem_all = eccq_attn_smem;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(eccq_attn_smem);
+  unsigned char* const upper = smem_all + (0x20000u - base);
+  unsigned char* smem = LUT ? upper : smem_all;   // merge area (and staging of the non-table variant)
+  const uint32_t tab = kLutTableAddr;
+  if (LUT) {
+    const uint8_t* one = reinterpret_cast<const uint8_t*>(pair_tab) + (CODEC == ECCQ_CODEC_H84 ? 256 : 0);   // hb(decode(c)), c = 0..255
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_all + (kLutTableAddr - base));
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) dst[(i >> 5) * 64 + (i & 31)] = (uint32_t)__ldg(one + (i >> 5)) << 8;
+    __syncthreads();
+  }
   const int G = a.Hq / g.H;
   const int npass = (G + 7) / 8;
-  const int h = blockIdx.y / npass;
-  const int pass = blockIdx.y - h * npass;
-  const int i = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grow = lane >> 2, quad = lane & 3;
+  const uint32_t lane4 = (uint32_t)lane * 4u | (LUT ? kLutTableAddr : 0u);   // see lut_byte
+  const int64_t page_bytes = (int64_t)g.bs * D;
+  unsigned char* wsm = !LUT ? smem + (size_t)warp * 2 * STAGE
+                            : (warp < kLutLowWarps ? smem_all + (size_t)warp * 2 * STAGE : upper + (size_t)(warp - kLutLowWarps) * 2 * STAGE);
+  const float* vsc_base = a.v_use_k_scales ? g.k_scales : g.v_scales;
+  FlagCount fc;
+  const int ny = g.H * npass;
+  const int nitems = LUT ? a.nsplit * ny * a.nseq : 1;
+#pragma unroll 1
+  for (int item = LUT ? (int)blockIdx.x : 0; item < nitems; item += LUT ? (int)gridDim.x : 1) {
+  // item = (i * ny + hy) * nsplit + split: consecutive CTAs walk the chunks of one (sequence, head)
+  const int split = LUT ? item % a.nsplit : (int)blockIdx.x;
+  const int hy = LUT ? (item / a.nsplit) % ny : (int)blockIdx.y;
+  const int i = LUT ? item / (a.nsplit * ny) : (int)blockIdx.z;
+  const int h = hy / npass;
+  const int pass = hy - h * npass;
   const int ctx = a.context_lens[i];
   const int c0 = split * a.chunk;
   const int c1 = min(ctx, c0 + a.chunk);
   const int g0 = pass * 8;
   const int ng = min(8, G - g0);
   const int32_t* bt = a.block_table + (int64_t)i * a.max_blocks;
-  const int64_t page_bytes = (int64_t)g.bs * D;
-  unsigned char* wsm = smem + (size_t)warp * 2 * STAGE;
-  const float* vsc_base = a.v_use_k_scales ? g.k_scales : g.v_scales;
 
   // ---- Q fragments (B operand of QK^T): head n = lane/4, dims quad*(D/4) + 4s + {0,1 | 2,3}; sm_scale*log2e folded in
   uint32_t qf[KS][2], qf_lo[PRECISE ? KS : 1][2];
@@ -113,7 +168,6 @@ __global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, A
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[mt][e] = 0.0f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};   // heads 2*quad, 2*quad+1
-  FlagCount fc;
   const bool do_count = COUNT && pass == 0;
 
   // tiles of this warp: first tile index (in units of 16 tokens) is c0/16 + warp, stride kMmaWarps
@@ -146,8 +200,8 @@ __global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, A
   if (tile < tile_end) cur_ok = stage_tile(tile, 0);
   cp_async_commit();
   int st = 0;
-  for (; tile < tile_end; tile += kMmaWarps, st ^= 1) {
-    const int ntile = tile + kMmaWarps;
+  for (; tile < tile_end; tile += NW, st ^= 1) {
+    const int ntile = tile + NW;
     bool next_ok = false;
     if (ntile < tile_end) next_ok = stage_tile(ntile, st ^ 1);
     cp_async_commit();
@@ -174,11 +228,19 @@ __global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, A
         const bool v0 = do_count && tok0 + grow < c1, v1 = do_count && tok0 + grow + 8 < c1;
 #pragma unroll
         for (int s = 0; s < KS; ++s) {
-          uint32_t f0 = 0, f1 = 0;
-          const uint32_t n0 = decode_word<CODEC, COUNT>(kr0[s], f0);
-          const uint32_t n1 = decode_word<CODEC, COUNT>(kr1[s], f1);
-          if (COUNT) { fc.add(v0 ? f0 : 0u); fc.add(v1 ? f1 : 0u); }
-          const uint32_t af[4] = {nib2_to_half2(n0, 0x4140), nib2_to_half2(n1, 0x4140), nib2_to_half2(n0, 0x4342), nib2_to_half2(n1, 0x4342)};
+          uint32_t af[4];
+          if (LUT_K) {
+            af[0] = half_pair(lut_byte<0>(tab, kr0[s], lane4), lut_byte<1>(tab, kr0[s], lane4));
+            af[1] = half_pair(lut_byte<0>(tab, kr1[s], lane4), lut_byte<1>(tab, kr1[s], lane4));
+            af[2] = half_pair(lut_byte<2>(tab, kr0[s], lane4), lut_byte<3>(tab, kr0[s], lane4));
+            af[3] = half_pair(lut_byte<2>(tab, kr1[s], lane4), lut_byte<3>(tab, kr1[s], lane4));
+          } else {
+            uint32_t f0 = 0, f1 = 0;
+            const uint32_t n0 = decode_word<CODEC, COUNT>(kr0[s], f0);
+            const uint32_t n1 = decode_word<CODEC, COUNT>(kr1[s], f1);
+            if (COUNT) { fc.add(v0 ? f0 : 0u); fc.add(v1 ? f1 : 0u); }
+            af[0] = nib2_to_half2(n0, 0x4140); af[1] = nib2_to_half2(n1, 0x4140); af[2] = nib2_to_half2(n0, 0x4342); af[3] = nib2_to_half2(n1, 0x4342);
+          }
           mma16816(s4, af, qf[s][0], qf[s][1]);
           if (PRECISE) mma16816(s4, af, qf_lo[s][0], qf_lo[s][1]);
         }
@@ -207,8 +269,10 @@ __global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, A
       p[3] = (m_run[1] == -INFINITY) ? 0.0f : exp2f(s4[3] - m_run[1]);
       l_run[0] = l_run[0] * alpha[0] + p[0] + p[2];   // per-lane partial sums; reduced over the 8 row-lanes at the end
       l_run[1] = l_run[1] * alpha[1] + p[1] + p[3];
+      if (__any_sync(0xFFFFFFFFu, alpha[0] != 1.0f || alpha[1] != 1.0f)) {   // the running maxima rarely move after the first tiles
 #pragma unroll
-      for (int mt = 0; mt < KS; ++mt) { o[mt][0] *= alpha[0]; o[mt][1] *= alpha[1]; o[mt][2] *= alpha[0]; o[mt][3] *= alpha[1]; }
+        for (int mt = 0; mt < KS; ++mt) { o[mt][0] *= alpha[0]; o[mt][1] *= alpha[1]; o[mt][2] *= alpha[0]; o[mt][3] *= alpha[1]; }
+      }
       // ---------------- P (x V scale) -> B fragments of PV
       const float vs0 = sVs[grow], vs1 = sVs[grow + 8];
       const float pv[4] = {p[0] * vs0, p[1] * vs0, p[2] * vs1, p[3] * vs1};
@@ -236,20 +300,37 @@ __global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, A
             vr[t][0] = x.x; vr[t][1 % VW] = x.y;
           }
           const bool vok = do_count && tok0 + toks[t] < c1;
+          if (!LUT_V) {
 #pragma unroll
-          for (int w = 0; w < VW; ++w) {
-            uint32_t f = 0;
-            vr[t][w] = decode_word<CODEC, COUNT>(vr[t][w], f);
-            if (COUNT) fc.add(vok ? f : 0u);
+            for (int w = 0; w < VW; ++w) {
+              uint32_t f = 0;
+              vr[t][w] = decode_word<CODEC, COUNT>(vr[t][w], f);
+              if (COUNT) fc.add(vok ? f : 0u);
+            }
           }
         }
 #pragma unroll
         for (int mt = 0; mt < KS; ++mt) {
           const int w = mt >> 1;
-          const uint32_t sel = (mt & 1) ? 0x7362u : 0x5140u;
-          const uint32_t x01 = __byte_perm(vr[0][w], vr[1][w], sel);   // {T0.b, T1.b, T0.b+1, T1.b+1}
-          const uint32_t x23 = __byte_perm(vr[2][w], vr[3][w], sel);
-          const uint32_t af[4] = {nib2_to_half2(x01, 0x4140), nib2_to_half2(x01, 0x4342), nib2_to_half2(x23, 0x4140), nib2_to_half2(x23, 0x4342)};
+          uint32_t af[4];
+          if (LUT_V) {   // operand pairs (T0.b, T1.b): two byte look-ups each, no gather
+            if (mt & 1) {
+              af[0] = half_pair(lut_byte<2>(tab, vr[0][w], lane4), lut_byte<2>(tab, vr[1][w], lane4));
+              af[1] = half_pair(lut_byte<3>(tab, vr[0][w], lane4), lut_byte<3>(tab, vr[1][w], lane4));
+              af[2] = half_pair(lut_byte<2>(tab, vr[2][w], lane4), lut_byte<2>(tab, vr[3][w], lane4));
+              af[3] = half_pair(lut_byte<3>(tab, vr[2][w], lane4), lut_byte<3>(tab, vr[3][w], lane4));
+            } else {
+              af[0] = half_pair(lut_byte<0>(tab, vr[0][w], lane4), lut_byte<0>(tab, vr[1][w], lane4));
+              af[1] = half_pair(lut_byte<1>(tab, vr[0][w], lane4), lut_byte<1>(tab, vr[1][w], lane4));
+              af[2] = half_pair(lut_byte<0>(tab, vr[2][w], lane4), lut_byte<0>(tab, vr[3][w], lane4));
+              af[3] = half_pair(lut_byte<1>(tab, vr[2][w], lane4), lut_byte<1>(tab, vr[3][w], lane4));
+            }
+          } else {
+            const uint32_t sel = (mt & 1) ? 0x7362u : 0x5140u;
+            const uint32_t x01 = __byte_perm(vr[0][w], vr[1][w], sel);   // {T0.b, T1.b, T0.b+1, T1.b+1}
+            const uint32_t x23 = __byte_perm(vr[2][w], vr[3][w], sel);
+            af[0] = nib2_to_half2(x01, 0x4140); af[1] = nib2_to_half2(x01, 0x4342); af[2] = nib2_to_half2(x23, 0x4140); af[3] = nib2_to_half2(x23, 0x4342);
+          }
           mma16816(o[mt], af, pb0, pb1);
           if (PRECISE) mma16816(o[mt], af, pl0, pl1);
         }
@@ -286,13 +367,13 @@ __global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, A
     }
   }
   __syncthreads();
-  for (int gi = warp; gi < ng; gi += kMmaWarps) {
+  for (int gi = warp; gi < ng; gi += NW) {
     float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < kMmaWarps; ++w) M = fmaxf(M, red[((size_t)w * 8 + gi) * RS + D]);
-    float f[kMmaWarps], L = 0.0f;
+    for (int w = 0; w < NW; ++w) M = fmaxf(M, red[((size_t)w * 8 + gi) * RS + D]);
+    float f[NW], L = 0.0f;
 #pragma unroll
-    for (int w = 0; w < kMmaWarps; ++w) {
+    for (int w = 0; w < NW; ++w) {
       const float mw = red[((size_t)w * 8 + gi) * RS + D];
       f[w] = (mw == -INFINITY) ? 0.0f : exp2f(mw - M);
       L += red[((size_t)w * 8 + gi) * RS + D + 1] * f[w];
@@ -302,12 +383,14 @@ __global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, A
     for (int d = lane; d < D; d += 32) {
       float acc = 0.0f;
 #pragma unroll
-      for (int w = 0; w < kMmaWarps; ++w) acc += red[((size_t)w * 8 + gi) * RS + d] * f[w];
+      for (int w = 0; w < NW; ++w) acc += red[((size_t)w * 8 + gi) * RS + d] * f[w];
       wsrow[d] = acc;
     }
     // the merge kernel works in natural-log units: m_ln = m_log2 * ln2
     if (lane == 0) { wsrow[D] = (M == -INFINITY) ? -INFINITY : M * 0.6931471805599453f; wsrow[D + 1] = L; }
   }
+  if (LUT) __syncthreads();   // the staging area is reused by the next item
+  }   // items
   if (COUNT) {
     const int idx[2] = {ECCQ_CTR_CORRECTED, ECCQ_CTR_DETECTED};
     const uint32_t val[2] = {fc.singles(), fc.doubles()};
@@ -316,27 +399,56 @@ __global__ void __launch_bounds__(kMmaThreads, 4) attn_mma_kernel(CacheGeom g, A
 }
 
 template <typename TQ, int CODEC, int D, bool PRECISE>
-static int launch_attn_mma(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+static int launch_attn_mma(const CacheGeom& g, AttnArgs& a, uint64_t* counters, cudaStream_t st) {
   const size_t stage = 2 * kTile * (D + 16) + 2 * kTile * 4;
-  const size_t smem = std::max<size_t>(kMmaWarps * 2 * stage, sizeof(float) * kMmaWarps * 8 * (D + 2));
   const int G = a.Hq / g.H;
   const int npass = (G + 7) / 8;
+  constexpr bool kHamming = CODEC == ECCQ_CODEC_H84 || CODEC == ECCQ_CODEC_H74;
+  static const int lut_env = [] { const char* v = std::getenv("ECCQ_ATTN_LUT"); return v && *v ? std::atoi(v) : 1; }();
+  if (kHamming && !a.count_errors && lut_env) {
+    // table variant: persistent, one 8-warp CTA per SM
+    const uint16_t* tab = ensure_pair_tables();
+    if (tab != nullptr) {
+      // a persistent CTA of kLutWarps warps needs items long enough to amortise the per-item pipeline fill and merge:
+      // coarsen the split-KV plan (the partial / merge protocol is unchanged, only fewer partials are written)
+      static const int coarsen = [] { const char* v = std::getenv("ECCQ_ATTN_LUT_COARSEN"); return v && *v ? std::atoi(v) : 4; }();
+      if (coarsen > 1 && a.nsplit > 1) {
+        a.chunk *= coarsen;
+        a.nsplit = (a.nsplit + coarsen - 1) / coarsen;
+      }
+      // dynamic window: everything up to the table's end at 0x20000 (the window starts at >= 0 and, with the 1 KB the
+      // system reserves, normally at 1024) + the upper staging / merge area
+      const size_t upper = std::max<size_t>((kLutWarps - kLutLowWarps) * 2 * stage, sizeof(float) * kLutWarps * 8 * (D + 2));
+      const size_t smem = 0x20000 + upper;
+      const int items = a.nsplit * g.H * npass * a.nseq;
+      auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<std::min(items, sm_count()), kLutWarps * 32, smem, st>>>(g, a, counters, tab);
+      };
+      constexpr int HC = kHamming ? CODEC : ECCQ_CODEC_H84;
+      if (lut_env == 2) go(attn_mma_kernel<TQ, HC, D, PRECISE, false, 2>);
+      else if (lut_env == 3) go(attn_mma_kernel<TQ, HC, D, PRECISE, false, 3>);
+      else go(attn_mma_kernel<TQ, HC, D, PRECISE, false, 1>);
+      return ECCQ_OK;
+    }
+  }
+  const size_t smem = std::max<size_t>(kMmaWarps * 2 * stage, sizeof(float) * kMmaWarps * 8 * (D + 2));
   dim3 grid(a.nsplit, g.H * npass, a.nseq);
   if (a.count_errors) {
-    auto kern = attn_mma_kernel<TQ, CODEC, D, PRECISE, true>;
+    auto kern = attn_mma_kernel<TQ, CODEC, D, PRECISE, true, 0>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kMmaThreads, smem, st>>>(g, a, counters);
+    kern<<<grid, kMmaThreads, smem, st>>>(g, a, counters, nullptr);
   } else {
-    auto kern = attn_mma_kernel<TQ, CODEC, D, PRECISE, false>;
+    auto kern = attn_mma_kernel<TQ, CODEC, D, PRECISE, false, 0>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kMmaThreads, smem, st>>>(g, a, counters);
+    kern<<<grid, kMmaThreads, smem, st>>>(g, a, counters, nullptr);
   }
   return ECCQ_OK;
 }
 
 // returns 1 when the tile kernel took the launch, 0 when the shape/codec needs the general kernel
 template <typename TQ>
-static int try_attn_mma(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+static int try_attn_mma(const CacheGeom& g, AttnArgs& a, uint64_t* counters, cudaStream_t st) {
   if (g.codec == ECCQ_CODEC_GOLAY || a.interp) return 0;
   if ((g.D != 64 && g.D != 128) || g.bs % kTile != 0 || a.chunk % kTile != 0) return 0;
   if (!aligned16(g.k_cache) || !aligned16(g.v_cache) || !aligned16(g.k_scales) || !aligned16(g.v_scales)) return 0;

@@ -35,6 +35,7 @@ inline int check_launch(const char* what) {
 struct DeviceState {
   bool tables = false;
   int sms = 0;
+  uint16_t* pair_tab = nullptr;   // 2 x 256-byte decode tables of the LUT attention kernel (H74, H84), see build_byte_table()
 };
 inline DeviceState& device_state() {
   static DeviceState st[64];
@@ -96,6 +97,26 @@ inline const GolayTables& host_golay_tables() {
   std::call_once(once, [] { build_golay_tables(t); });
   return t;
 }
+// ---- byte tables of the LUT attention kernel ---------------------------------------------------------------------
+// entry[c] = hb(decode(c)) where decode() is the corrected nibble of the codeword byte (hamming84_triton.py:116-209: single
+// errors corrected, double errors keep the raw nibble; hamming74_triton.py:129-160: every non-zero syndrome corrected, bit 7
+// ignored) and hb(n) is the HIGH byte of the fp16 number n - 8 -- its low byte is zero for every integer in [-8, 7].
+inline uint32_t host_hamming_decode_nibble(uint32_t c, bool h84) {
+  static const int syn_to_bit[8] = {-1, 4, 5, 0, 6, 1, 2, 3};   // config.py:131-161
+  const uint32_t b0 = c & 1, b1 = (c >> 1) & 1, b2 = (c >> 2) & 1, b3 = (c >> 3) & 1, b4 = (c >> 4) & 1, b5 = (c >> 5) & 1, b6 = (c >> 6) & 1;
+  const uint32_t syn = (b4 ^ b0 ^ b1 ^ b3) | ((b5 ^ b0 ^ b2 ^ b3) << 1) | ((b6 ^ b1 ^ b2 ^ b3) << 2);
+  const uint32_t perr = __builtin_popcount(c & 0xFF) & 1;   // overall parity mismatch (Hamming(8,4))
+  uint32_t n = c & 0xF;
+  const bool fix = h84 ? (syn != 0 && perr) : (syn != 0);
+  if (fix && syn_to_bit[syn] >= 0 && syn_to_bit[syn] < 4) n ^= 1u << syn_to_bit[syn];
+  return n;
+}
+inline void build_byte_table(uint8_t* t, bool h84) {
+  static const uint8_t hb[16] = {0xC8, 0xC7, 0xC6, 0xC5, 0xC4, 0xC2, 0xC0, 0xBC, 0x00, 0x3C, 0x40, 0x42, 0x44, 0x45, 0x46, 0x47};
+  for (uint32_t c = 0; c < 256; ++c) t[c] = hb[host_hamming_decode_nibble(c, h84)];
+}
+const uint16_t* ensure_pair_tables();   // device pointer to the two 256-byte tables [H74][H84]; defined in eccq_lib.cu
+
 int ensure_tables();  // defined in eccq_lib.cu next to the __device__ symbol
 
 inline FastInject make_fast_inject(float ber, uint64_t seed) {

@@ -19,6 +19,22 @@ int ensure_tables() {
   return ECCQ_OK;
 }
 
+const uint16_t* ensure_pair_tables() {
+  DeviceState& s = device_state();
+  if (s.pair_tab) return s.pair_tab;
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (s.pair_tab) return s.pair_tab;
+  std::vector<uint16_t> h(256);   // 512 bytes
+  build_byte_table(reinterpret_cast<uint8_t*>(h.data()), false);
+  build_byte_table(reinterpret_cast<uint8_t*>(h.data()) + 256, true);
+  uint16_t* d = nullptr;
+  // synchronous on purpose: once per device, before the first launch that needs it
+  if (cudaMalloc(&d, h.size() * sizeof(uint16_t)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+  s.pair_tab = d;
+  return d;
+}
+
 }  // namespace eccq
 
 #include "eccq_codecs.cu"
