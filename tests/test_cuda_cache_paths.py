@@ -131,3 +131,111 @@ def test_fast_injector_window_kernel_formats():
             bits = n * n_bits
             assert abs(flips - bits * 2e-2) < 5 * (bits * 2e-2) ** 0.5 + 3
             assert torch.equal(out, ck.inject_bit_errors_fast(x, 2e-2, n_bits, seed=7))
+
+
+@pytest.mark.parametrize("codec", ["hamming84", "golay"])
+def test_fused_roundtrip_properties_at_c3_size(oracle, codec):
+    """Size-independent properties of the fused write -> read path at BASELINE config-3 size (16 x 8192 tokens x 8 kv-heads
+    x 128 = 134 M values per tensor, random page placement): one flipped bit per codeword is corrected back to the clean
+    read (corrected == number of codewords); two flipped bits are all detected and, with interpolation, all replaced;
+    sampled rows agree with the oracle."""
+    from eccq_b200 import _lib
+    from eccq_b200.kv_cache import SimpleBlockManager, read_cache
+    B, S, H, D, bs = 16, 8192, 8, 128, 16
+    nblk = B * S // bs
+    lib = _lib.load()
+    P = _lib.ptr
+    sp = _lib.c_void_p(torch.cuda.current_stream().cuda_stream)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    k = torch.randn(B, S, H * D, device="cuda", dtype=torch.float16, generator=gen)
+    v = torch.randn(B, S, H * D, device="cuda", dtype=torch.float16, generator=gen)
+    m = SimpleBlockManager(nblk, bs, 1, H, D, device="cuda", codec=codec)
+    m.block_table = torch.randperm(nblk, generator=torch.Generator().manual_seed(3)).to(torch.int32).view(B, S // bs).cuda()
+    cl = torch.full((B,), S, dtype=torch.int32, device="cuda")
+    cw = (D + 2) // 3 if codec == "golay" else D
+    ncw = 2 * B * S * H * cw
+
+    def write(km=None, vm=None):
+        inj = _lib.INJECT_MASK if km is not None else _lib.INJECT_NONE
+        _lib.check(lib.eccq_cache_write(m.desc(), P(k), P(v), _lib.ECCQ_F16, P(m.block_table), S // bs, None, B, S, 0, inj, P(km), P(vm),
+                                        0.0, 0, 0, None, sp), "cache_write")
+
+    def read(interp=False):
+        ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+        kf, vf = read_cache(m.k_cache, m.v_cache, m.k_scales, m.v_scales, m.block_table, cl, 0, bs, D, codec, use_interpolation=interp,
+                            out_dtype=torch.float16, counters=ctr)
+        return kf, vf, ctr.tolist()
+
+    write()
+    k0, v0, c0 = read()
+    assert c0[0] == 0 and c0[1] == 0
+    # sampled rows against the oracle (first and last sequence, a few tokens)
+    for b, t in ((0, 0), (0, 4097), (B - 1, S - 1)):
+        row = k[b, t].float().cpu().numpy().reshape(H, D)
+        q, sc = oracle.quantize_int4(row)
+        assert np.array_equal(k0[b, t].cpu().numpy(), oracle.dequantize_int4(q, sc).astype(np.float16))
+    nbits = 24 if codec == "golay" else 8
+    mdt = torch.int32 if codec == "golay" else torch.uint8
+    bit = torch.randint(0, nbits if codec == "golay" else 7, (B, S, H, cw), device="cuda", dtype=torch.int32)
+    one = torch.bitwise_left_shift(torch.ones_like(bit), bit).to(mdt)
+    write(one, one)
+    k1, v1, c1 = read()
+    assert torch.equal(k1, k0) and torch.equal(v1, v0)
+    assert c1[0] == ncw and c1[1] == 0
+    if codec == "hamming84":
+        two = (one.to(torch.int32) | torch.bitwise_left_shift(torch.ones_like(bit), (bit + 1) % 8)).to(mdt)
+        write(two, two)
+        _, _, c2 = read(interp=True)
+        assert c2[0] == 0 and c2[1] == ncw and c2[5] == ncw
+    else:
+        three = torch.full_like(one, 0x800401)    # three flips per codeword: still corrected
+        write(three, three)
+        k3, v3, c3 = read()
+        assert torch.equal(k3, k0) and torch.equal(v3, v0) and c3[0] == 3 * ncw and c3[1] == 0
+
+
+def test_decode_attention_corrects_single_flips_at_32k_context():
+    """ECC-fused paged decode attention at the C5 context length (32 768 tokens, GQA 32/8, random pages): one flipped bit in
+    EVERY codeword of K and V leaves the output bit-identical to the clean cache's (table prologue), both prologues agree
+    with each other within the fp16 tolerance, and the counted decode reports every codeword as corrected."""
+    from eccq_b200 import _lib
+    from eccq_b200.kv_cache import SimpleBlockManager, paged_attention_ecc
+    B, ctx, Hq, H, D, bs = 2, 32768, 32, 8, 128, 16
+    nblk = B * ctx // bs
+    lib = _lib.load()
+    P = _lib.ptr
+    sp = _lib.c_void_p(torch.cuda.current_stream().cuda_stream)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    k = torch.randn(B, ctx, H * D, device="cuda", dtype=torch.float16, generator=gen)
+    v = torch.randn(B, ctx, H * D, device="cuda", dtype=torch.float16, generator=gen)
+    q = torch.randn(B, Hq, D, device="cuda", dtype=torch.float16, generator=gen)
+    m = SimpleBlockManager(nblk, bs, 1, H, D, device="cuda", codec="hamming84")
+    m.block_table = torch.randperm(nblk, generator=torch.Generator().manual_seed(4)).to(torch.int32).view(B, ctx // bs).cuda()
+    cl = torch.tensor([ctx, ctx - 1000], dtype=torch.int32, device="cuda")
+
+    def write(mask=None):
+        inj = _lib.INJECT_MASK if mask is not None else _lib.INJECT_NONE
+        _lib.check(lib.eccq_cache_write(m.desc(), P(k), P(v), _lib.ECCQ_F16, P(m.block_table), ctx // bs, None, B, ctx, 0, inj, P(mask), P(mask),
+                                        0.0, 0, 0, None, sp), "cache_write")
+
+    def attend(counters=None):
+        return paged_attention_ecc(q, m.k_cache, m.v_cache, m.block_table, cl, m.k_scales, 0, bs, v_scales=m.v_scales, counters=counters)
+
+    write()
+    clean = attend()
+    bit = torch.randint(0, 8, (B, ctx, H, D), device="cuda", dtype=torch.int32)
+    one = torch.bitwise_left_shift(torch.ones_like(bit), bit).to(torch.uint8)
+    write(one)
+    noisy = attend()
+    assert torch.equal(noisy, clean)
+    ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+    counted = attend(ctr)                       # SWAR prologue (flags needed for the counters)
+    assert (counted.float() - clean.float()).abs().max().item() < 2e-3
+    # every codeword of the attended context is a single error: data-bit and parity-bit flips alike have syndrome != 0
+    # except flips of the overall parity bit (bit 7), which are "parity only" and not counted (hamming84_triton.py:185-187)
+    attended = int(cl.sum().item()) * H * D * 2
+    par_only = 0
+    for b in range(B):
+        n = int(cl[b].item())
+        par_only += 2 * int((bit[b, :n] == 7).sum().item())
+    assert int(ctr[0]) == attended - par_only and int(ctr[1]) == 0
