@@ -128,6 +128,17 @@ int eccq_cache_read(const eccq_cache_desc* c, const int32_t* block_table, int ma
                     int nseq, int out_stride_tokens, int layer, int use_interpolation, int out_dtype, void* k_out, void* v_out,
                     uint8_t* nib_out_k, uint8_t* nib_out_v, uint64_t* counters, void* stream);
 
+/* Decode [+ temporally interpolate] the pages of ONE layer into corrected INT4 pages of a one-layer cache with the same
+ * paged layout (k_pages / v_pages: uint8 [num_blocks, 1, Hkv, block_size*D], one nibble per byte; k/v_page_scales: fp32
+ * [num_blocks, 1, Hkv, block_size], copies of the row scales).  This is the decode + interpolate half of ECCBackend.attend
+ * (ecc_shim.py:979-1038) for q_len == 1: paged decode attention with interpolation runs its INT4 tile path over the corrected
+ * pages (neighbours along the token axis span pages and tiles, so they are resolved once here, by the streaming read kernel).
+ * Counters: CORRECTED / DETECTED / INTERPOLATED as eccq_cache_read.  ECCQ_EUNSUPPORTED for Golay or geometries other than
+ * head_dim 128/64 with 16/32-token blocks (the caller then uses eccq_paged_decode_attention's general path). */
+int eccq_cache_correct_pages(const eccq_cache_desc* c, const int32_t* block_table, int max_blocks, const int32_t* context_lens,
+                             int nseq, int layer, int use_interpolation, uint8_t* k_pages, uint8_t* v_pages,
+                             float* k_page_scales, float* v_page_scales, uint64_t* counters, void* stream);
+
 /* ---- ECC-fused paged decode attention ------------------------------------------------------------------- */
 /* paged_attention_ecc, kv_cache/attention_ecc.py:620-780 (kernel :264-426), generalised to GQA (kv_head = q_head/group,
  * SURVEY Q13), to hamming74/golay, to temporal interpolation, and split over the context (FlashDecoding).

@@ -22,6 +22,7 @@ ECCQ_F32, ECCQ_F16, ECCQ_BF16 = 0, 1, 2
 CODEC_H74, CODEC_H84, CODEC_GOLAY, CODEC_INT4 = 0, 1, 2, 3
 CODEC_IDS = {"hamming74": CODEC_H74, "hamming84": CODEC_H84, "golay": CODEC_GOLAY, "int4": CODEC_INT4}
 CODEC_BITS = {"hamming74": 7, "hamming84": 8, "golay": 24, "int4": 4}
+ECCQ_EUNSUPPORTED = -3
 CTR_CORRECTED, CTR_DETECTED, CTR_FLIPPED, CTR_AFFECTED, CTR_VALUES, CTR_INTERPOLATED, NCOUNTERS = 0, 1, 2, 3, 4, 5, 8
 INJECT_NONE, INJECT_MASK, INJECT_PHILOX_REF, INJECT_PHILOX_FAST = 0, 1, 2, 3
 INJECT_MODES = {"none": INJECT_NONE, "mask": INJECT_MASK, "philox_ref": INJECT_PHILOX_REF, "philox_fast": INJECT_PHILOX_FAST}
@@ -64,6 +65,7 @@ _SIGNATURES = {
     "eccq_cache_write": (c_int, [POINTER(CacheDesc), _P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, _P,
                                  c_float, c_int64, c_int64, _P, _P]),
     "eccq_cache_read": (c_int, [POINTER(CacheDesc), _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "eccq_cache_correct_pages": (c_int, [POINTER(CacheDesc), _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "eccq_attention_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "eccq_paged_decode_attention": (c_int, [POINTER(CacheDesc), _P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_float,
                                             c_int, c_int, c_int, _P, c_int64, _P, _P]),

@@ -281,7 +281,18 @@ __global__ void __launch_bounds__(256, (INTERP && CODEC == ECCQ_CODEC_H84) ? 2 :
 #pragma unroll
           for (int k = 0; k < 4; ++k) carry[k] = last[k];
         }
-        if (nvalid == BS) {
+        if (a.paged_nib) {
+          // corrected INT4 pages of a one-layer cache with the same paged layout + a copy of the row scales
+          const int64_t pg = (int64_t)blk * g.H + h;
+          float* sco = kv ? a.scv_out : a.sck_out;
+#pragma unroll
+          for (int s = 0; s < SPL; ++s) {
+            if (slot0 + s < nvalid) {
+              st_stream(nout + pg * page_bytes + (slot0 + s) * D + c * 16, make_uint4(nib[s][0], nib[s][1], nib[s][2], nib[s][3]));
+              if (c == 0) sco[pg * BS + slot0 + s] = sc[s];
+            }
+          }
+        } else if (nvalid == BS) {
 #pragma unroll
           for (int s = 0; s < SPL; ++s) {
             if (out) dequant_store16<TO>(out + obase + s * ostride, nib[s], sc[s]);

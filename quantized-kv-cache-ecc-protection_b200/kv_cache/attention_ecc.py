@@ -21,6 +21,25 @@ from .._lib import check, device_of, load, ptr, require_cuda, stream_of
 _workspaces: dict = {}
 
 
+_page_scratch: dict = {}
+
+
+def _corrected_pages(device, num_blocks, hkv, block_size, head_dim):
+    """Scratch one-layer INT4 cache (pages + scales for K and V) for decode attention with interpolation."""
+    key = (device, num_blocks, hkv, block_size, head_dim)
+    t = _page_scratch.get(key)
+    if t is None:
+        _page_scratch.clear()     # one geometry at a time: the scratch is as large as one layer of the cache
+        # zero-filled like the cache itself: slots past a ragged context are staged with their tile (and masked), so their
+        # scales must be finite
+        t = (torch.zeros(num_blocks, 1, hkv, block_size * head_dim, dtype=torch.uint8, device=device),
+             torch.zeros(num_blocks, 1, hkv, block_size * head_dim, dtype=torch.uint8, device=device),
+             torch.zeros(num_blocks, 1, hkv, block_size, dtype=torch.float32, device=device),
+             torch.zeros(num_blocks, 1, hkv, block_size, dtype=torch.float32, device=device))
+        _page_scratch[key] = t
+    return t
+
+
 def _workspace(device, nbytes: int) -> torch.Tensor:
     ws = _workspaces.get(device)
     if ws is None or ws.numel() < nbytes:
@@ -63,10 +82,28 @@ def paged_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_sc
     max_blocks = bt.shape[1]
     desc = _lib.cache_desc(k_cache, v_cache, k_scales, v_scales, D, block_size, codec)
     out = torch.empty_like(qd)
+    interp = bool(use_interpolation) and codec == "hamming84"     # the reference interpolates hamming84 only
     with device_of(qd):
         lib = load()
         nbytes = lib.eccq_attention_workspace_bytes(B, Hq, D, max_blocks * block_size)
         ws = _workspace(qd.device, nbytes)
+        if interp:
+            # temporal neighbours span pages: resolve them once with the streaming read kernel into corrected INT4 pages
+            # (same paged layout, one layer), then attend over those with the INT4 tile path.  Falls through to the
+            # general kernel for geometries the streaming kernel does not cover.
+            nb, _, hkv, _ = k_cache.shape
+            kp, vp, ksp, vsp = _corrected_pages(qd.device, nb, hkv, block_size, D)
+            rc = lib.eccq_cache_correct_pages(desc, ptr(bt), max_blocks, ptr(cl), B, int(layer_idx), 1, ptr(kp), ptr(vp), ptr(ksp),
+                                              ptr(vsp), ptr(counters), stream_of(qd))
+            if rc == 0:
+                pdesc = _lib.cache_desc(kp, vp, ksp, ksp if v_use_k else vsp, D, block_size, "int4")
+                check(lib.eccq_paged_decode_attention(pdesc, ptr(qd), ptr(out), _lib.dtype_code(qd.dtype), ptr(bt), max_blocks, ptr(cl),
+                                                      B, Hq, 0, float(sm_scale), 0, int(v_use_k), 0, ptr(ws), ws.numel(), None,
+                                                      stream_of(qd)), "paged_attention_ecc")
+                return out if out.dtype == query.dtype else out.to(query.dtype)
+            if rc != _lib.ECCQ_EUNSUPPORTED:
+                check(rc, "cache_correct_pages")
+        use_interpolation = interp
         check(lib.eccq_paged_decode_attention(desc, ptr(qd), ptr(out), _lib.dtype_code(qd.dtype), ptr(bt), max_blocks, ptr(cl), B, Hq,
                                               int(layer_idx), float(sm_scale), int(bool(use_interpolation)), int(v_use_k),
                                               int(counters is not None), ptr(ws), ws.numel(), ptr(counters), stream_of(qd)),
