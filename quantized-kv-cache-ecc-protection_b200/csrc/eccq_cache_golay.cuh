@@ -241,7 +241,29 @@ __global__ void __launch_bounds__(256, 3) cache_read_golay2_kernel(CacheGeom g, 
               f[3 * k + 2] = (__uint_as_float(0x4B000000u | ((x >> 8) & 0xFu)) - 8388616.0f) * sc;
             }
           }
-          if (out) {
+          if (a.paged_nib) {
+            // eccq_cache_correct_pages: corrected nibbles as INT4 pages of a one-layer cache (row = D bytes) + row scales
+            uint8_t* pages = cur.kv ? a.nib_v : a.nib_k;
+            const int64_t pg = (int64_t)cur.blk * g.H + cur.h;
+            uint32_t w[6] = {0, 0, 0, 0, 0, 0};   // 24 nibble bytes (f[] holds scaled values: the nibbles come from the codewords again)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t c = k < ncw ? src[k] : 0u;
+              const uint32_t e = s_syn[(uint32_t)s_par[c & 0xFFFu] ^ ((c >> 12) & 0xFFFu)];
+              const uint32_t x = c ^ e;
+#pragma unroll
+              for (int q = 0; q < 3; ++q) {
+                const int b = 3 * k + q;                       // byte index inside the 24-byte run
+                w[b >> 2] |= ((x >> (4 * q)) & 0xFu) << (8 * (b & 3));
+              }
+            }
+            const int nval = min(24, D - 24 * gi);
+            uint2* dst = reinterpret_cast<uint2*>(pages + pg * ((int64_t)BS * D) + t * D + 24 * gi);
+            dst[0] = make_uint2(w[0], w[1]);
+            if (nval > 8) dst[1] = make_uint2(w[2], w[3]);
+            if (nval > 16) dst[2] = make_uint2(w[4], w[5]);
+            if (gi == 0) (cur.kv ? a.scv_out : a.sck_out)[pg * BS + t] = sc;
+          } else if (out) {
             TO* dst = out + obase + t * ostride + 24 * gi;
             constexpr int VPC = 16 / (int)sizeof(TO);   // values per 16-byte chunk
             const int nval = min(24, D - 24 * gi);

@@ -87,13 +87,13 @@ def paged_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_sc
         lib = load()
         nbytes = lib.eccq_attention_workspace_bytes(B, Hq, D, max_blocks * block_size)
         ws = _workspace(qd.device, nbytes)
-        if interp:
-            # temporal neighbours span pages: resolve them once with the streaming read kernel into corrected INT4 pages
-            # (same paged layout, one layer), then attend over those with the INT4 tile path.  Falls through to the
-            # general kernel for geometries the streaming kernel does not cover.
+        if interp or codec == "golay":
+            # temporal neighbours span pages (and Golay codewords span values): resolve them once with the streaming read
+            # kernels into corrected INT4 pages (same paged layout, one layer), then attend over those with the INT4 tile
+            # path.  Falls through to the general kernel for geometries the streaming kernels do not cover.
             nb, _, hkv, _ = k_cache.shape
             kp, vp, ksp, vsp = _corrected_pages(qd.device, nb, hkv, block_size, D)
-            rc = lib.eccq_cache_correct_pages(desc, ptr(bt), max_blocks, ptr(cl), B, int(layer_idx), 1, ptr(kp), ptr(vp), ptr(ksp),
+            rc = lib.eccq_cache_correct_pages(desc, ptr(bt), max_blocks, ptr(cl), B, int(layer_idx), int(interp), ptr(kp), ptr(vp), ptr(ksp),
                                               ptr(vsp), ptr(counters), stream_of(qd))
             if rc == 0:
                 pdesc = _lib.cache_desc(kp, vp, ksp, ksp if v_use_k else vsp, D, block_size, "int4")
