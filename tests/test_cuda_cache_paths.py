@@ -239,3 +239,54 @@ def test_decode_attention_corrects_single_flips_at_32k_context():
         n = int(cl[b].item())
         par_only += 2 * int((bit[b, :n] == 7).sum().item())
     assert int(ctr[0]) == attended - par_only and int(ctr[1]) == 0
+
+
+@pytest.mark.parametrize("codec,interp", [("hamming84", True), ("hamming84", False), ("hamming74", False), ("golay", False)])
+def test_correct_pages_matches_oracle(oracle, codec, interp):
+    """eccq_cache_correct_pages: corrected (+ interpolated) INT4 pages and row scales of one layer, against the oracle's decode
+    of the gathered context; geometries outside the streaming kernels answer ECCQ_EUNSUPPORTED."""
+    from eccq_b200 import _lib
+    from eccq_b200.kv_cache import ECCBackend, ECCShimConfig, SimpleBlockManager
+    D, bs, H, L, S = 128, 16, 3, 2, 77
+    nblk = -(-S // bs) + 3
+    cfg = ECCShimConfig(codec=codec, ber=0.03, inject_errors=True, block_size=bs, num_blocks=nblk, use_interpolation=interp, seed=7)
+    mgr = SimpleBlockManager(nblk, bs, L, H, D, device="cuda", codec=codec)
+    mgr.free_blocks = [int(b) for b in np.random.default_rng(2).permutation(nblk)]
+    be = ECCBackend(mgr, cfg, H)
+    rng = np.random.default_rng(17)
+    k = rng.standard_normal((1, S, H * D)).astype(np.float32)
+    v = rng.standard_normal((1, S, H * D)).astype(np.float32)
+    be.write(dev(k).half(), dev(v).half(), layer_idx=1, seq_id=0)
+    lib = _lib.load()
+    P = _lib.ptr
+    kp = torch.zeros(nblk, 1, H, bs * D, dtype=torch.uint8, device="cuda")
+    vp, ksp = torch.zeros_like(kp), torch.zeros(nblk, 1, H, bs, dtype=torch.float32, device="cuda")
+    vsp = torch.zeros_like(ksp)
+    ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+    cl = torch.tensor([S - 5], dtype=torch.int32, device="cuda")
+    bt = mgr.block_table[:1].contiguous()
+    rc = lib.eccq_cache_correct_pages(mgr.desc(), P(bt), bt.shape[1], P(cl), 1, 1, int(interp), P(kp), P(vp), P(ksp), P(vsp), P(ctr),
+                                      _lib.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.eccq_last_error()
+    # oracle: gather + decode the same context
+    oc = oracle.PagedCache(nblk, bs, L, H, D, codec)
+    oc.k_cache[:] = mgr.k_cache.cpu().numpy(); oc.v_cache[:] = mgr.v_cache.cpu().numpy()
+    oc.k_scales[:] = mgr.k_scales.cpu().numpy(); oc.v_scales[:] = mgr.v_scales.cpu().numpy()
+    btn = bt[0].cpu().numpy()
+    kc, vc, ks, vs = oracle.cache_gather(oc, 1, btn, S - 5)
+    kd, c1, d1 = oracle.decode_rows(kc, codec, D, interp)
+    vd, c2, d2 = oracle.decode_rows(vc, codec, D, interp)
+    kpn, vpn, kspn = kp.cpu().numpy(), vp.cpu().numpy(), ksp.cpu().numpy()
+    for t in range(S - 5):
+        blk, slot = int(btn[t // bs]), t % bs
+        assert np.array_equal(kpn[blk, 0, :, slot * D:(slot + 1) * D], kd[t]), t
+        assert np.array_equal(vpn[blk, 0, :, slot * D:(slot + 1) * D], vd[t]), t
+        assert np.array_equal(kspn[blk, 0, :, slot], ks[t])
+    assert (int(ctr[0]), int(ctr[1])) == (c1 + c2, d1 + d2)
+    # a geometry the streaming kernels do not cover
+    m2 = SimpleBlockManager(4, 4, 1, 2, 32, device="cuda", codec=codec)
+    z8 = torch.zeros(4, 1, 2, 4 * 32, dtype=torch.uint8, device="cuda")
+    zf = torch.zeros(4, 1, 2, 4, dtype=torch.float32, device="cuda")
+    bt2 = torch.zeros(1, 4, dtype=torch.int32, device="cuda")
+    rc = lib.eccq_cache_correct_pages(m2.desc(), P(bt2), 4, P(cl), 1, 0, 0, P(z8), P(z8.clone()), P(zf), P(zf.clone()), None, None)
+    assert rc == _lib.ECCQ_EUNSUPPORTED
