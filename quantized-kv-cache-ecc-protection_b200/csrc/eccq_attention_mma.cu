@@ -1,4 +1,4 @@
-// eccq_attention_mma.cu -- ECC-fused paged decode attention, tensor-core tile version (v1).
+// eccq_attention_mma.cu -- ECC-fused paged decode attention, tensor-core tile version.
 //
 // One CTA = (sequence, kv-head, context chunk), four warps; each warp walks 16-token tiles (one tile never straddles a
 // page: block_size % 16 == 0).  Per tile:
@@ -14,8 +14,10 @@
 // The GQA group (<= 8 q-heads) rides on the N dimension, so each codeword is decoded once for the whole group.
 // With fp32 queries Q and P are split hi+lo (two MMAs) so the 1e-4 bar of the reference's fp32 tests holds.
 //
-// This version issues legacy HMMA; the decode prologue (ALU pipe), not the tensor pipe, bounds it.  DESIGN.md describes
-// the tcgen05/TMEM variant that shares this staging and partial/merge protocol.
+// The contraction issues legacy HMMA (under 2 % of the instruction stream); the kernel is bound by the decode prologue and the
+// tile loop around it, not by the tensor pipe.  Two prologues share this tile loop: SWAR (hamming_sel4, used when decode
+// errors are counted) and a shared-memory table (default, see attn_mma_kernel<..., LUT>).  Interpolation and Golay reach this
+// kernel through eccq_cache_correct_pages (corrected INT4 pages).  DESIGN.md 4.6 has the measurements and the tcgen05 note.
 #include "eccq_internal.h"
 
 namespace eccq {

@@ -2,7 +2,7 @@
 """Run ONE kernel variant of the hot path a few times (for ncu captures and quick timings).
 
     python tools/prof_case.py <case> [reps]
-    cases: copy h84enc h84dec write0 write3 write3lo read0 read1 readint4 writeg readg attn attni attng   (C3 / C5 shapes)
+    cases: copy h84enc h84dec write0 write3 write3lo read0 read1 readint4 writeg readg attn attni attng attn4   (C3 / C5 shapes)
 Prints the median CUDA-event time and algorithmic GB/s when not under a profiler."""
 import statistics
 import sys
@@ -93,7 +93,7 @@ elif case.startswith(("write", "read")):
               vals * (cwb + 4 / D + 2))
 else:
     Bq, ctx, HQ = 8, 32768, 32
-    codec = "golay" if case == "attng" else "hamming84"
+    codec = "golay" if case == "attng" else "int4" if case == "attn4" else "hamming84"
     nblk = Bq * ctx // BS
     m = SimpleBlockManager(nblk, BS, 1, H, D, device=dev, codec=codec)
     m.block_table = torch.randperm(nblk).to(torch.int32).view(Bq, ctx // BS).to(dev)
