@@ -95,17 +95,22 @@ __device__ __forceinline__ void load_scales(const float* p, float (&sc)[SPL]) {
 // INTERP = true: the next page is prefetched into registers (it is also the right neighbour of this page's last row);
 // 2 CTAs per SM.  INTERP = false: less arithmetic per byte, so the smoother memory traffic of 3 CTAs per SM (<= 85
 // registers, pages loaded at the top of their own iteration) wins over the deeper per-warp prefetch.
-template <typename TO, int CODEC, bool INTERP, int C, int SPL>
+// HP = heads per warp: with head_dim 64 and 16-token blocks a page is only 1 KB, so a warp takes the pages of TWO adjacent
+// heads of a block (contiguous in the cache): each half-warp runs the 4-lanes-per-row x 4-slots mapping on its own head,
+// which halves the per-page overhead.  Lane shuffles that cross the half-warp only reach values that are overwritten
+// (first / last lane group of a page).
+template <typename TO, int CODEC, bool INTERP, int C, int SPL, int HP = 1>
 __global__ void __launch_bounds__(256, (INTERP && CODEC == ECCQ_CODEC_H84) ? 2 : 3) cache_read2_kernel(CacheGeom g, ReadArgs a, int nblk_logical, int chunk, int head_fastest,
                                                               uint64_t* counters) {
-  constexpr int D = 16 * C, GROUPS = 32 / C, BS = GROUPS * SPL;
+  constexpr int D = 16 * C, HL = 32 / HP, GROUPS = HL / C, BS = GROUPS * SPL;   // HL = lanes per head
   constexpr bool kHamming = CODEC == ECCQ_CODEC_H84 || CODEC == ECCQ_CODEC_H74;
   constexpr bool kInterp = INTERP && CODEC == ECCQ_CODEC_H84;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   constexpr int64_t page_bytes = (int64_t)BS * D;
   const int lane = threadIdx.x & 31;
+  const int hsel = lane / HL, hbase = hsel * HL;   // which of the warp's heads this lane works on; its first lane
   const int c = lane & (C - 1);
-  const int grp = lane / C;
+  const int grp = (lane - hbase) / C;
   const int slot0 = grp * SPL;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -114,7 +119,8 @@ __global__ void __launch_bounds__(256, (INTERP && CODEC == ECCQ_CODEC_H84) ? 2 :
   // one contiguous region of the output ([token][head][D]) at a time, which keeps the DRAM accesses of a CTA page-local.
   const uint32_t nblk = (uint32_t)nblk_logical;
   const uint32_t nchunk = (nblk + chunk - 1) / chunk;
-  const uint32_t units = 2u * (uint32_t)a.nseq * (uint32_t)g.H * nchunk;
+  const uint32_t HU = (uint32_t)g.H / HP;   // head units per (sequence, tensor)
+  const uint32_t units = 2u * (uint32_t)a.nseq * HU * nchunk;
   FlagCount fc;
 
   for (uint32_t u = warp; u < units; u += nwarps) {
@@ -122,16 +128,17 @@ __global__ void __launch_bounds__(256, (INTERP && CODEC == ECCQ_CODEC_H84) ? 2 :
     uint32_t ikv;
     int h, j;
     if (head_fastest) {          // u = ((i*2 + kv)*nchunk + chunk_index)*H + h
-      const uint32_t rest = u / (uint32_t)g.H;
-      h = (int)(u - rest * (uint32_t)g.H);
+      const uint32_t rest = u / HU;
+      h = (int)(u - rest * HU);
       ikv = rest / nchunk;
       j = (int)(rest - ikv * nchunk) * chunk;
     } else {                     // u = ((i*2 + kv)*H + h)*nchunk + chunk_index
       const uint32_t rest = u / nchunk;
       j = (int)(u - rest * nchunk) * chunk;
-      ikv = rest / (uint32_t)g.H;
-      h = (int)(rest - ikv * (uint32_t)g.H);
+      ikv = rest / HU;
+      h = (int)(rest - ikv * HU);
     }
+    h = h * HP + hsel;
     const int kv = (int)(ikv & 1u);
     const int i = (int)(ikv >> 1);
     const int ctx = min(a.context_lens[i], a.T);
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(256, (INTERP && CODEC == ECCQ_CODEC_H84) ? 2 :
         if constexpr (kInterp) {
           uint32_t last[4];   // this page's last row before interpolation = the next page's left neighbour
 #pragma unroll
-          for (int k = 0; k < 4; ++k) last[k] = __shfl_sync(FULL, nib[SPL - 1][k], (GROUPS - 1) * C + c);
+          for (int k = 0; k < 4; ++k) last[k] = __shfl_sync(FULL, nib[SPL - 1][k], hbase + (GROUPS - 1) * C + c);
           uint32_t anyd = 0;
 #pragma unroll
           for (int s = 0; s < SPL; ++s) anyd |= flag[s][0] | flag[s][1] | flag[s][2] | flag[s][3];
@@ -229,8 +236,8 @@ __global__ void __launch_bounds__(256, (INTERP && CODEC == ECCQ_CODEC_H84) ? 2 :
                                 ((flag[SPL - 1][0] | flag[SPL - 1][1] | flag[SPL - 1][2] | flag[SPL - 1][3]) & M01) != 0u;
             if (__any_sync(FULL, e_next)) {
               uint4 x;
-              x.x = __shfl_sync(FULL, rawn[0].x, c); x.y = __shfl_sync(FULL, rawn[0].y, c);
-              x.z = __shfl_sync(FULL, rawn[0].z, c); x.w = __shfl_sync(FULL, rawn[0].w, c);
+              x.x = __shfl_sync(FULL, rawn[0].x, hbase + c); x.y = __shfl_sync(FULL, rawn[0].y, hbase + c);
+              x.z = __shfl_sync(FULL, rawn[0].z, hbase + c); x.w = __shfl_sync(FULL, rawn[0].w, hbase + c);
               uint32_t nn[4], nf[4];
               decode_words4<CODEC>(x, nn, nf);
               if (grp == GROUPS - 1) {
