@@ -1,6 +1,8 @@
 """Config 2 in miniature on the GPU: a random-init 2-layer GPT-2 (weights from the fixture) under
 patch_model_with_ecc_attention(backend="cuda"), every ECC mode, BER 0 and 1e-2 -- logits, loss and get_ecc_stats against
 the numbers the REFERENCE produced on the same weights and token ids (tests/golden/make_golden.py gpt2)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -124,7 +126,36 @@ def test_cuda_phase_timer_reports_bandwidth():
     from eccq_b200.evaluation import TimingStats, cuda_phase_timer, cuda_timer
     x = torch.randint(0, 16, (1 << 24,), dtype=torch.uint8, device="cuda")
     st = TimingStats(values_processed=x.numel())
+    hamming84_encode(x)          # first call in a process pays module load / allocator warm-up
     with cuda_phase_timer(st, "encode", bytes_moved=2 * x.numel()):
         hamming84_encode(x)
     assert st.encode_ns > 0 and st.gbps("encode") > 1.0
     assert cuda_timer(lambda: hamming84_encode(x), warmup=2, repeats=5) > 0
+
+
+def test_sweep_driver_on_the_cuda_backend(gpt2):
+    """the sweep that drives the path (evaluation/sweep.py of the reference) with backend='cuda' -- every
+    protected mode x BER cell runs, counters behave (none at BER 0, corrections grow with the BER), a cell reproduces the
+    reference's loss on the same weights / ids / seed, seeds aggregate."""
+    from eccq_b200.evaluation.sweep import SweepConfig, generate_clean_logits, run_single_trial, run_sweep
+    model, ids, g = gpt2
+    texts = [ids[:1], ids[:1, :40]]
+    clean = generate_clean_logits(model, None, texts, max_length=64)
+    cfg = SweepConfig(ber_levels=[0.0, 1e-3, 1e-2], seeds=[42, 101], max_length=64, num_blocks=8, clean_logits=clean)
+    res = run_sweep(model, None, texts, cfg)
+    assert len(res.trials) == 4 * 3 * 2
+    for mode in cfg.cache_modes:
+        cells = res.aggregated[mode]
+        assert cells[0.0].errors_corrected_mean == 0 and cells[0.0].errors_detected_mean == 0
+        assert cells[0.0].perplexity_std == 0.0                         # no injection: seeds cannot matter
+        assert cells[1e-2].errors_corrected_mean > cells[1e-3].errors_corrected_mean > 0
+        assert 0.0 <= cells[1e-2].top5_accuracy_mean <= 1.0 and cells[1e-2].kl_divergence_mean >= 0.0
+        assert math.isfinite(cells[1e-2].perplexity_mean)
+    # the full-length text alone, hamming84 @ 1e-2, seed 42 is the golden cell of test_patched_gpt2_matches_reference
+    cfg1 = SweepConfig(max_length=64, num_blocks=8)
+    t = run_single_trial(model, None, [ids[:1]], "int4-hamming84", 1e-2, 42, cfg1)
+    assert abs(math.log(t.perplexity) - float(g["hamming84_ber0.01_loss"])) < 1e-4
+    ref = g["hamming84_ber0.01_stats"]
+    assert [t.injection_count, t.errors_corrected, t.errors_detected, t.total_values] == ref[:4].tolist()
+    with pytest.raises(ValueError):
+        run_single_trial(model, None, texts, "fp16", 0.0, 42, cfg1)       # unprotected comparison codecs: out of scope
