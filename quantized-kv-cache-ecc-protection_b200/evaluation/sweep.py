@@ -34,6 +34,7 @@ MODE_CONFIG = {
 }
 CACHE_MODE_ORDER = ["int4-hamming", "int4-hamming84", "int4-hamming84-interp", "int12-golay"]
 BER_LEVELS = [0.0, 1e-4, 1e-3, 1e-2]
+BER_LEVELS_EXTENDED = [0.0, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2]      # constants.py:93
 SEEDS = [42, 101, 997, 1999, 4999, 7919, 10007, 15073, 21001, 31337]
 
 
@@ -130,13 +131,22 @@ def _token_ids(text, tokenizer, max_length: int, device):
     return tokenizer(text, return_tensors="pt", truncation=True, max_length=max_length)["input_ids"].to(device)
 
 
-def generate_clean_logits(model, tokenizer, texts, max_length: int = 256, device="cuda") -> List[Optional[torch.Tensor]]:
-    """Logits of the unpatched model per text (metrics.py:230-256); pass as SweepConfig.clean_logits."""
+def generate_clean_logits(model, tokenizer, texts, max_length: int = 256, device="cuda",
+                          keep_on_device: bool = True) -> List[Optional[torch.Tensor]]:
+    """Logits of the unpatched model per text (metrics.py:230-256); pass as SweepConfig.clean_logits.
+
+    The reference parks them on the CPU and re-uploads [S, vocab] fp32 (51 MB for GPT-2 at S=256) per text per trial, which
+    costs more than the forward pass; 180 GB of HBM holds them for any sample count the sweep uses, so they stay resident
+    unless `keep_on_device=False`."""
     out = []
     with torch.no_grad():
         for text in texts:
             ids = _token_ids(text, tokenizer, max_length, device)
-            out.append(None if ids is None or ids.size(1) < 2 else model(ids, use_cache=False).logits[0].float().cpu())
+            if ids is None or ids.size(1) < 2:
+                out.append(None)
+                continue
+            logits = model(ids, use_cache=False).logits[0].float()
+            out.append(logits if keep_on_device else logits.cpu())
     return out
 
 
@@ -150,36 +160,46 @@ def run_single_trial(model, tokenizer, texts, cache_mode: str, ber: float, seed:
                         block_size=config.block_size, use_interpolation=mode["use_interpolation"], backend="cuda",
                         injector=config.injector)
     device = next(model.parameters()).device
-    total_loss, total_tokens = 0.0, 0
-    kls, hits, positions, sample_ppls = [], 0, 0, []
+    # per-text results stay on the device until the trial ends: one host sync per trial instead of four per text, so the
+    # host keeps launching the next forward pass while the GPU finishes this one
+    rows, lens, positions = [], [], 0
+    zero = torch.zeros((), device=device)
+    # token ids go up before the first forward pass: a pageable host-to-device copy blocks until the stream drains
+    all_ids = [_token_ids(text, tokenizer, config.max_length, device) for text in texts]
     with torch.no_grad(), patch_model_with_ecc_attention(model, ecc, num_blocks=ecc.num_blocks):
-        for n, text in enumerate(texts):
-            ids = _token_ids(text, tokenizer, config.max_length, device)
+        for n, ids in enumerate(all_ids):
             if ids is None or ids.size(1) < 2:
                 continue
             reset_ecc_cache(model)
             out = model(ids, labels=ids, use_cache=True)
-            loss = out.loss
-            if torch.isnan(loss) or torch.isinf(loss):
-                sample_ppls.append(float("inf"))
-                continue
             seq_len = ids.size(1)
-            total_loss += loss.item() * seq_len
-            total_tokens += seq_len
-            sample_ppls.append(float(math.exp(min(loss.item(), 700.0))))
             logits = out.logits[0].float()
+            hit, kl = zero, zero.new_full((), float("nan"))
             if config.compute_top5:
                 top5 = torch.topk(logits[:-1], k=5, dim=-1).indices
-                hits += int((top5 == ids[0, 1:, None]).any(-1).sum().item())
-                positions += seq_len - 1
+                hit = (top5 == ids[0, 1:, None]).any(-1).sum().float()
             if config.compute_kl_divergence and config.clean_logits is not None and config.clean_logits[n] is not None:
                 clean = config.clean_logits[n].to(device)
                 m = min(clean.size(0), logits.size(0))
                 lp, lq = F.log_softmax(clean[:m], dim=-1), F.log_softmax(logits[:m], dim=-1)
-                kl = (lp.exp() * (lp - lq)).sum(-1).mean().item()
-                if not (math.isnan(kl) or math.isinf(kl)):
-                    kls.append(kl)
+                kl = (lp.exp() * (lp - lq)).sum(-1).mean()
+            rows.append(torch.stack((out.loss.float(), hit, kl)))
+            lens.append(seq_len)
         stats = get_ecc_stats(model)
+    total_loss, total_tokens, hits = 0.0, 0, 0
+    kls, sample_ppls = [], []
+    for (loss, hit, kl), seq_len in zip(torch.stack(rows).tolist() if rows else [], lens):
+        if math.isnan(loss) or math.isinf(loss):          # such a text counts as catastrophic and nothing else
+            sample_ppls.append(float("inf"))
+            continue
+        total_loss += loss * seq_len
+        total_tokens += seq_len
+        sample_ppls.append(float(math.exp(min(loss, 700.0))))
+        if config.compute_top5:
+            hits += int(hit)
+            positions += seq_len - 1
+        if not (math.isnan(kl) or math.isinf(kl)):
+            kls.append(kl)
     ppl = float("inf") if total_tokens == 0 else float(math.exp(min(total_loss / total_tokens, 700.0)))
     corrected, detected = int(stats.get("errors_corrected", 0)), int(stats.get("errors_detected", 0))
     events = corrected + detected

@@ -128,7 +128,7 @@ def read_cache(k_cache, v_cache, k_scales, v_scales, block_table, context_lens, 
         lens = cl.tolist()
         T, ragged = (max(lens), min(lens) != max(lens)) if lens else (0, False)
     else:
-        T, ragged = int(max_context), True
+        T, ragged = int(max_context), nseq > 1      # one sequence: its context IS the longest
     H = k_cache.shape[2]
     dev = k_cache.device
     if out is not None:

@@ -170,6 +170,7 @@ class ECCBackend:
         self._injection_count = 0
         self._total_values = 0
         self._flip_masks = None
+        self._ctx_lens = None          # (host list, device int32 tensor) of the last attend()
         # the reference's Triton decode fast path (hamming84, no interpolation) updates no counters (Q12); keep its numbers
         self.count_decode_errors = not (config.codec == "hamming84" and not config.use_interpolation)
 
@@ -253,7 +254,9 @@ class ECCBackend:
         if max(lens) == 0:
             return torch.zeros_like(q)
         nseq = len(lens)
-        cl = torch.tensor(lens, dtype=torch.int32).to(q.device, non_blocking=True)
+        if self._ctx_lens is None or self._ctx_lens[0] != lens:      # every layer of one forward pass asks for the same lengths
+            self._ctx_lens = (lens, torch.tensor(lens, dtype=torch.int32).to(q.device, non_blocking=True))
+        cl = self._ctx_lens[1]
         bt = m.block_table[seq_id:seq_id + nseq]
         if Sq == 1:
             # fused paged decode attention for every codec (the reference: hamming84 without interpolation only)
@@ -272,19 +275,18 @@ class ECCBackend:
             return out.unsqueeze(2)
         dt = q.dtype if q.dtype in (torch.float32, torch.float16, torch.bfloat16) else torch.float32
         k, v = read_cache(m.k_cache, m.v_cache, m.k_scales, m.v_scales, bt, cl, layer_idx, m.block_size, D, cfg.codec,
-                          use_interpolation=cfg.use_interpolation, out_dtype=dt, counters=self._counters)
+                          use_interpolation=cfg.use_interpolation, out_dtype=dt, counters=self._counters, max_context=max(lens))
         return self._run_attention(q, k, v)
 
     def _run_attention(self, q, k, v):
         """ecc_shim.py:1138-1164: GQA expand + SDPA, causal (top-left) when q_len > 1. k, v: [nseq, ctx, Hkv, D]."""
         k = k.permute(0, 2, 1, 3)
         v = v.permute(0, 2, 1, 3)
-        if self.num_kv_groups > 1:
-            k = k.repeat_interleave(self.num_kv_groups, dim=1)
-            v = v.repeat_interleave(self.num_kv_groups, dim=1)
         if k.shape[0] != q.shape[0]:
             k, v = k.expand(q.shape[0], -1, -1, -1), v.expand(q.shape[0], -1, -1, -1)
-        return F.scaled_dot_product_attention(q, k.to(q.dtype), v.to(q.dtype), is_causal=q.shape[2] > 1)
+        # the GQA expansion happens inside SDPA (no Hq-sized copy of K/V, which the reference makes with repeat_interleave)
+        return F.scaled_dot_product_attention(q, k.to(q.dtype), v.to(q.dtype), is_causal=q.shape[2] > 1,
+                                              enable_gqa=self.num_kv_groups > 1)
 
 
 def _get_attention_params(attn):

@@ -25,9 +25,13 @@ def _backend(codec, interp, ber, dims, injector="philox_ref", append=False):
 
 @pytest.mark.parametrize("codec,interp", MODES)
 @pytest.mark.parametrize("ber", [0.0, 0.05])
-def test_backend_matches_reference_shim(golden, codec, interp, ber):
+@pytest.mark.parametrize("short_ref", ["1", "0"])
+def test_backend_matches_reference_shim(golden, codec, interp, ber, short_ref, monkeypatch):
     """Cache bytes, scales, attention outputs and counters equal the reference's ECCBackend on the same inputs,
-    including the fault-injection stream (bit-exact)."""
+    including the fault-injection stream (bit-exact).  Short writes with the reference's Philox stream take the
+    one-warp-per-row kernel (latency), long ones the tiled kernel: ECCQ_WRITE_SHORT_REF=0 forces the tiled kernel so
+    both routes are pinned to the same golden image."""
+    monkeypatch.setenv("ECCQ_WRITE_SHORT_REF", short_ref)
     g = golden("shim_vectors")
     dims = tuple(int(v) for v in g["dims"])
     B, S, Hq, Hkv, D, L, bs, nblk = dims

@@ -157,5 +157,9 @@ def test_sweep_driver_on_the_cuda_backend(gpt2):
     assert abs(math.log(t.perplexity) - float(g["hamming84_ber0.01_loss"])) < 1e-4
     ref = g["hamming84_ber0.01_stats"]
     assert [t.injection_count, t.errors_corrected, t.errors_detected, t.total_values] == ref[:4].tolist()
+    from eccq_b200.evaluation.monte_carlo import MonteCarloConfig, run_monte_carlo_experiment
+    mc = MonteCarloConfig(cache_modes=["int4-hamming84"], ber_levels=[1e-2], seeds=[42], max_length=64, num_blocks=8)
+    r = run_monte_carlo_experiment(model, None, mc, [ids[:1]], verbose=False)
+    assert r.aggregated["int4-hamming84"][1e-2].perplexity_mean == t.perplexity and r.trials[0].kl_divergence > 0
     with pytest.raises(ValueError):
         run_single_trial(model, None, texts, "fp16", 0.0, 42, cfg1)       # unprotected comparison codecs: out of scope

@@ -74,6 +74,20 @@ def test_config_and_wrappers_reject_bad_input_like_the_reference():
     assert bt.shape == (2, 7) and (bt == -1).all()
 
 
+def test_monte_carlo_config_maps_onto_a_cuda_sweep():
+    """evaluation/experiments/monte_carlo.py:31-72 of the reference with backend="cuda"."""
+    from eccq_b200.evaluation.monte_carlo import MonteCarloConfig
+    from eccq_b200.evaluation.sweep import SweepConfig, get_mode_config
+    mc = MonteCarloConfig(seeds=[42, 101, 997], ber_levels=[0.0, 1e-2])
+    sc = mc.to_sweep_config(clean_logits=["x"])
+    assert isinstance(sc, SweepConfig) and sc.backend == "cuda" and sc.seeds == [42, 101, 997] and sc.aggregate_seeds
+    assert sc.cache_modes == ["int4-hamming", "int4-hamming84", "int4-hamming84-interp", "int12-golay"] and sc.clean_logits == ["x"]
+    assert MonteCarloConfig().ber_levels == [0.0, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2] and len(MonteCarloConfig().seeds) == 10
+    assert get_mode_config("int4-hamming84-interp") == {"codec": "hamming84", "use_interpolation": True}
+    with pytest.raises(ValueError, match="Unknown cache mode"):
+        get_mode_config("fp16")
+
+
 def test_timing_containers():
     from eccq_b200.evaluation import AggregatedTimingStats, TimingContext, TimingStats
     s = TimingStats(values_processed=1_000_000)
