@@ -126,13 +126,15 @@ class device_of:
     """Make the tensor's device current for the duration of a call (per-device table upload, SM count)."""
 
     def __init__(self, t: torch.Tensor):
-        self.guard = torch.cuda.device(t.device)
+        # already current (the single-GPU-per-process case): nothing to switch, nothing to restore
+        self.guard = None if t.device.index == torch.cuda.current_device() else torch.cuda.device(t.device)
 
     def __enter__(self):
-        self.guard.__enter__()
+        if self.guard is not None:
+            self.guard.__enter__()
 
     def __exit__(self, *exc):
-        return self.guard.__exit__(*exc)
+        return self.guard.__exit__(*exc) if self.guard is not None else False
 
 
 def new_counters(device) -> torch.Tensor:

@@ -121,6 +121,7 @@ class SimpleBlockManager:
         self.v_cache = torch.zeros(shape, dtype=self.cache_dtype, device=device)
         self.k_scales = torch.zeros(num_blocks, num_layers, num_kv_heads, block_size, dtype=torch.float32, device=device)
         self.v_scales = torch.zeros_like(self.k_scales)
+        self._desc = None
         self.free_blocks = list(range(num_blocks))
         self.seq_to_blocks, self.seq_to_len = {}, {}
         self.max_seqs, self.max_blocks_per_seq = 32, num_blocks
@@ -156,7 +157,10 @@ class SimpleBlockManager:
             t.zero_()
 
     def desc(self):
-        return _lib.cache_desc(self.k_cache, self.v_cache, self.k_scales, self.v_scales, self.head_dim, self.block_size, self.codec)
+        if self._desc is None:      # the four buffers live as long as the manager
+            self._desc = _lib.cache_desc(self.k_cache, self.v_cache, self.k_scales, self.v_scales, self.head_dim, self.block_size,
+                                         self.codec)
+        return self._desc
 
 
 class ECCBackend:

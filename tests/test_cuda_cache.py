@@ -196,3 +196,22 @@ def test_block_manager_and_stats_api():
         ECCShimConfig(backend="triton")
     with pytest.raises(NotImplementedError):
         SimpleBlockManager(8, 4, 2, 2, 16, device="cuda", codec="fp16")
+
+
+@pytest.mark.parametrize("codec", ["hamming84", "golay"])
+def test_empty_write_and_empty_context_are_noops(codec):
+    """Zero tokens in: nothing is written, no counter moves, attention over an empty context is zeros (Q14 fixed) and a read
+    of zero sequences / zero tokens returns empty tensors -- no zero-sized launch reaches the driver."""
+    from eccq_b200.kv_cache import read_cache
+    dims = (1, 0, 4, 2, 64, 2, 16, 8)
+    be, mgr = _backend(codec, False, 0.01, dims)
+    k = torch.zeros(1, 0, 2 * 64, device="cuda", dtype=torch.float16)
+    be.write(k, k, layer_idx=0)
+    assert mgr.get_context_len(0) == 0 and not mgr.k_cache.any() and not mgr.k_scales.any()
+    assert (be._bits_flipped, be._errors_corrected, be._errors_detected) == (0, 0, 0)
+    q = torch.randn(1, 4, 1, 64, device="cuda", dtype=torch.float16)
+    assert not be.attend(q, layer_idx=0).any()
+    cl = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ko, vo = read_cache(mgr.k_cache, mgr.v_cache, mgr.k_scales, mgr.v_scales, mgr.block_table[:1], cl, 0, 16, 64, codec)
+    assert ko.shape == (1, 0, 2, 64) and vo.shape == (1, 0, 2, 64)
+    torch.cuda.synchronize()
