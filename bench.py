@@ -295,6 +295,7 @@ def run_ours(args):
         b = step_no[0] & 1
         step_no[0] += 1
         images[0].seq_to_len.clear()   # every step writes positions [0, S) of its 16 sequences again
+        images[0].seq_layer_len.clear()
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[b])          # the write that last read this buffer pair has finished
             kd2[b].copy_(kh, non_blocking=True)

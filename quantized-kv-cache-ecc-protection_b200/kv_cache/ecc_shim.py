@@ -124,6 +124,7 @@ class SimpleBlockManager:
         self._desc = None
         self.free_blocks = list(range(num_blocks))
         self.seq_to_blocks, self.seq_to_len = {}, {}
+        self.seq_layer_len = {}      # (seq_id, layer) -> tokens that layer has appended (ECCShimConfig(append=True))
         self.max_seqs, self.max_blocks_per_seq = 32, num_blocks
         self.block_table = torch.full((self.max_seqs, self.max_blocks_per_seq), -1, dtype=torch.int32, device=device)
 
@@ -152,6 +153,7 @@ class SimpleBlockManager:
             self.free_blocks.extend(blocks)
         self.seq_to_blocks.clear()
         self.seq_to_len.clear()
+        self.seq_layer_len.clear()
         self.block_table.fill_(-1)
         for t in (self.k_cache, self.v_cache, self.k_scales, self.v_scales):
             t.zero_()
@@ -226,9 +228,12 @@ class ECCBackend:
             inject = INJECT_MODES[cfg.injector]
         inj_base = self._injection_count
         if cfg.append:
-            start = torch.tensor([m.get_context_len(seq_id + b) for b in range(B)], dtype=torch.int32)
+            # every layer appends at ITS OWN length: the layers of one forward pass write the same positions one after another
+            starts = [m.seq_layer_len.get((seq_id + b, layer_idx), 0) for b in range(B)]
             for b in range(B):
-                m.allocate(seq_id + b, int(start[b]) + S)
+                m.allocate(seq_id + b, max(m.get_context_len(seq_id + b), starts[b] + S))
+                m.seq_layer_len[(seq_id + b, layer_idx)] = starts[b] + S
+            start = torch.tensor(starts, dtype=torch.int32)
             bt, start_dev, nseq = m.block_table[seq_id:seq_id + B], start.to(k.device, non_blocking=True), B
         else:
             # reference semantics (Q11): every batch row lands on positions [0,S) of `seq_id`, so only the last row
@@ -252,7 +257,7 @@ class ECCBackend:
         B, Hq, Sq, D = q.shape
         m, cfg = self.manager, self.config
         if cfg.append:
-            lens = [m.get_context_len(seq_id + b) for b in range(B)]
+            lens = [m.seq_layer_len.get((seq_id + b, layer_idx), 0) for b in range(B)]
         else:
             lens = [m.get_context_len(seq_id)]
         if max(lens) == 0:

@@ -163,3 +163,26 @@ def test_sweep_driver_on_the_cuda_backend(gpt2):
     assert r.aggregated["int4-hamming84"][1e-2].perplexity_mean == t.perplexity and r.trials[0].kl_divergence > 0
     with pytest.raises(ValueError):
         run_single_trial(model, None, texts, "fp16", 0.0, 42, cfg1)       # unprotected comparison codecs: out of scope
+
+
+@pytest.mark.parametrize("codec,interp", MODES)
+def test_incremental_decode_equals_one_shot_prefill(gpt2, codec, interp):
+    """SURVEY 8 f3 on a model: with `append=True` a prefill followed by single-token steps (fused decode attention over the
+    protected cache, q_len == 1) reproduces the logits of one prefill over the whole sequence (fused read + SDPA) -- the
+    per-(token, head) quantisation makes the cache image identical, so only fp32 summation order differs."""
+    from eccq_b200.kv_cache import ECCShimConfig, get_ecc_stats, patch_model_with_ecc_attention, reset_ecc_cache
+    model, ids, _ = gpt2
+    S, T = ids.shape[1], ids.shape[1] - 5
+    cfg = ECCShimConfig(codec=codec, num_blocks=8, use_interpolation=interp, append=True)
+    with torch.no_grad(), patch_model_with_ecc_attention(model, cfg, num_blocks=8):
+        full = model(ids[:1]).logits
+        reset_ecc_cache(model)
+        steps = [model(ids[:1, :T]).logits]
+        for t in range(T, S):
+            steps.append(model(ids[:1, t:t + 1], position_ids=torch.tensor([[t]], device="cuda")).logits)
+        st = get_ecc_stats(model)
+    inc = torch.cat(steps, dim=1)
+    assert inc.shape == full.shape
+    assert (inc - full).abs().max().item() < 2e-4 * max(1.0, full.abs().max().item())
+    assert st["errors_corrected"] == 0 and st["errors_detected"] == 0
+    assert st["total_values"] == 2 * 2 * S * 2 * 16            # K+V x layers x tokens x heads x head_dim: every token written once
