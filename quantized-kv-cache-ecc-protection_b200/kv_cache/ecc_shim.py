@@ -408,9 +408,12 @@ class ECCPagedAttentionShim(nn.Module):
         q = self._split(self.q_proj(hidden_states), self.num_heads)
         k = self._split(self.k_proj(hidden_states), self.num_kv_heads)
         v = self._split(self.v_proj(hidden_states), self.num_kv_heads)
-        if position_ids is None:
-            position_ids = torch.arange(s, device=hidden_states.device).unsqueeze(0).expand(b, -1)
-        cos, sin = self.rotary_emb(v, position_ids)
+        if position_embeddings is not None:      # recent transformers hand the layer (cos, sin) of the right positions
+            cos, sin = position_embeddings
+        else:
+            if position_ids is None:
+                position_ids = torch.arange(s, device=hidden_states.device).unsqueeze(0).expand(b, -1)
+            cos, sin = self.rotary_emb(v, position_ids)
         while cos.dim() < 4:
             cos, sin = cos.unsqueeze(0 if cos.dim() < 2 else 1), sin.unsqueeze(0 if sin.dim() < 2 else 1)
         if cos.shape[1] not in (1, q.shape[1]):

@@ -186,3 +186,25 @@ def test_incremental_decode_equals_one_shot_prefill(gpt2, codec, interp):
     assert (inc - full).abs().max().item() < 2e-4 * max(1.0, full.abs().max().item())
     assert st["errors_corrected"] == 0 and st["errors_detected"] == 0
     assert st["total_values"] == 2 * 2 * S * 2 * 16            # K+V x layers x tokens x heads x head_dim: every token written once
+
+
+def test_llama_gqa_incremental_decode_equals_prefill():
+    """The same on the LLaMA layout (RoPE positions, GQA 4:2, fused decode attention with two query heads per kv head)."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from eccq_b200.kv_cache import ECCShimConfig, patch_model_with_ecc_attention, reset_ecc_cache
+    torch.manual_seed(1)
+    cfg = LlamaConfig(hidden_size=256, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                      vocab_size=128, max_position_embeddings=128)
+    model = LlamaForCausalLM(cfg).eval().cuda()
+    S, T = 37, 30
+    ids = torch.randint(0, 128, (1, S), device="cuda")
+    for codec, interp in (("hamming84", False), ("hamming84", True), ("golay", False)):
+        ecc = ECCShimConfig(codec=codec, num_blocks=8, use_interpolation=interp, append=True)
+        with torch.no_grad(), patch_model_with_ecc_attention(model, ecc, num_blocks=8):
+            full = model(ids).logits
+            reset_ecc_cache(model)
+            steps = [model(ids[:, :T]).logits]
+            for t in range(T, S):
+                steps.append(model(ids[:, t:t + 1], position_ids=torch.tensor([[t]], device="cuda")).logits)
+        inc = torch.cat(steps, dim=1)
+        assert (inc - full).abs().max().item() < 2e-4 * max(1.0, full.abs().max().item()), codec
