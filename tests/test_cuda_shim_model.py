@@ -188,14 +188,16 @@ def test_incremental_decode_equals_one_shot_prefill(gpt2, codec, interp):
     assert st["total_values"] == 2 * 2 * S * 2 * 16            # K+V x layers x tokens x heads x head_dim: every token written once
 
 
-def test_llama_gqa_incremental_decode_equals_prefill():
-    """The same on the LLaMA layout (RoPE positions, GQA 4:2, fused decode attention with two query heads per kv head)."""
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 6e-2), (torch.float16, 1e-2)])
+def test_llama_gqa_incremental_decode_equals_prefill(dtype, tol):
+    """The same on the LLaMA layout (RoPE positions, GQA 4:2, fused decode attention with two query heads per kv head), in
+    fp32 and in the half-precision dtypes a served model runs in (K/V reach the cache, and come back, in the model's dtype)."""
     from transformers import LlamaConfig, LlamaForCausalLM
     from eccq_b200.kv_cache import ECCShimConfig, patch_model_with_ecc_attention, reset_ecc_cache
     torch.manual_seed(1)
     cfg = LlamaConfig(hidden_size=256, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
                       vocab_size=128, max_position_embeddings=128)
-    model = LlamaForCausalLM(cfg).eval().cuda()
+    model = LlamaForCausalLM(cfg).eval().cuda().to(dtype)
     S, T = 37, 30
     ids = torch.randint(0, 128, (1, S), device="cuda")
     for codec, interp in (("hamming84", False), ("hamming84", True), ("golay", False)):
@@ -206,5 +208,28 @@ def test_llama_gqa_incremental_decode_equals_prefill():
             steps = [model(ids[:, :T]).logits]
             for t in range(T, S):
                 steps.append(model(ids[:, t:t + 1], position_ids=torch.tensor([[t]], device="cuda")).logits)
-        inc = torch.cat(steps, dim=1)
-        assert (inc - full).abs().max().item() < 2e-4 * max(1.0, full.abs().max().item()), codec
+        inc = torch.cat(steps, dim=1).float()
+        assert inc.dtype == torch.float32 and steps[0].dtype == dtype and torch.isfinite(inc).all()
+        assert (inc - full.float()).abs().max().item() < tol * max(1.0, full.float().abs().max().item()), codec
+
+
+def test_batched_append_equals_per_sequence_runs(gpt2):
+    """append=True maps batch row b to sequence b: a batched prefill + batched single-token steps give, row by row, the logits
+    of running each sequence alone (the reference's write lets later rows overwrite earlier ones, Q11)."""
+    from eccq_b200.kv_cache import ECCShimConfig, get_ecc_stats, patch_model_with_ecc_attention, reset_ecc_cache
+    model, ids, _ = gpt2
+    g = torch.Generator().manual_seed(5)
+    B, S, T = 3, 40, 36
+    batch = torch.randint(0, 100, (B, S), generator=g).cuda()
+    pos = lambda t: torch.full((B, 1), t, device="cuda")
+    for codec, interp in (("hamming84", True), ("golay", False)):
+        cfg = ECCShimConfig(codec=codec, num_blocks=16, use_interpolation=interp, append=True)
+        with torch.no_grad(), patch_model_with_ecc_attention(model, cfg, num_blocks=16):
+            together = torch.cat([model(batch[:, :T]).logits] + [model(batch[:, t:t + 1], position_ids=pos(t)).logits for t in range(T, S)], dim=1)
+            st = get_ecc_stats(model)
+            assert st["sequences"] == B and st["total_values"] == 2 * 2 * B * S * 2 * 16
+            alone = []
+            for b in range(B):
+                reset_ecc_cache(model)
+                alone.append(model(batch[b:b + 1]).logits)
+        assert (together - torch.cat(alone)).abs().max().item() < 2e-4, codec
