@@ -93,14 +93,15 @@ __device__ __forceinline__ void load_scales(const float* p, float (&sc)[SPL]) {
 
 
 // INTERP = true: the next page is prefetched into registers (it is also the right neighbour of this page's last row);
-// 2 CTAs per SM.  INTERP = false: less arithmetic per byte, so the smoother memory traffic of 3 CTAs per SM (<= 85
-// registers, pages loaded at the top of their own iteration) wins over the deeper per-warp prefetch.
+// INTERP = false: pages loaded at the top of their own iteration.  2 CTAs per SM (128 registers) everywhere except the
+// 1 KB-page mapping without interpolation (C=4, SPL=2), which fits 80 registers and is 20 % faster at 3 CTAs per SM; the
+// other non-interpolating variants spill ~100 B at 80 registers and run 12-15 % faster at 2 (same-box A/B).
 // HP = heads per warp: with head_dim 64 and 16-token blocks a page is only 1 KB, so a warp takes the pages of TWO adjacent
 // heads of a block (contiguous in the cache): each half-warp runs the 4-lanes-per-row x 4-slots mapping on its own head,
 // which halves the per-page overhead.  Lane shuffles that cross the half-warp only reach values that are overwritten
 // (first / last lane group of a page).
 template <typename TO, int CODEC, bool INTERP, int C, int SPL, int HP = 1>
-__global__ void __launch_bounds__(256, (INTERP && CODEC == ECCQ_CODEC_H84) ? 2 : 3) cache_read2_kernel(CacheGeom g, ReadArgs a, int nblk_logical, int chunk, int head_fastest,
+__global__ void __launch_bounds__(256, (C == 4 && SPL == 2 && !(INTERP && CODEC == ECCQ_CODEC_H84)) ? 3 : 2) cache_read2_kernel(CacheGeom g, ReadArgs a, int nblk_logical, int chunk, int head_fastest,
                                                               uint64_t* counters) {
   constexpr int D = 16 * C, HL = 32 / HP, GROUPS = HL / C, BS = GROUPS * SPL;   // HL = lanes per head
   constexpr bool kHamming = CODEC == ECCQ_CODEC_H84 || CODEC == ECCQ_CODEC_H74;
