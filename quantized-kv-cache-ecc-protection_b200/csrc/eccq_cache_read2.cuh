@@ -96,6 +96,8 @@ __device__ __forceinline__ void load_scales(const float* p, float (&sc)[SPL]) {
 // INTERP = false: pages loaded at the top of their own iteration.  2 CTAs per SM (128 registers) everywhere except the
 // 1 KB-page mapping without interpolation (C=4, SPL=2), which fits 80 registers and is 20 % faster at 3 CTAs per SM; the
 // other non-interpolating variants spill ~100 B at 80 registers and run 12-15 % faster at 2 (same-box A/B).
+// Prefetching the next page in the non-interpolating variants as well (the registers are there at 2 CTAs per SM, and ncu
+// shows them waiting on their loads: long-scoreboard 3.5 cycles per issue) measured 9-17 % SLOWER -- not adopted.
 // HP = heads per warp: with head_dim 64 and 16-token blocks a page is only 1 KB, so a warp takes the pages of TWO adjacent
 // heads of a block (contiguous in the cache): each half-warp runs the 4-lanes-per-row x 4-slots mapping on its own head,
 // which halves the per-page overhead.  Lane shuffles that cross the half-warp only reach values that are overwritten
