@@ -3,5 +3,5 @@
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 mkdir -p "$HERE/lib"
-exec nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -split-compile=0 -Xcompiler -fPIC -shared \
+exec nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -split-compile=8 -Xcompiler -fPIC -shared \
   -I"$HERE/../include" -I"$HERE/csrc" "$@" "$HERE/csrc/eccq_lib.cu" -o "$HERE/lib/libeccq_sm100a.so"
