@@ -1,5 +1,7 @@
 #!/bin/sh
 # Build libeccq_sm100a.so in-tree (sm_100a only). Usage: sh build.sh [extra nvcc flags]
+# One plain nvcc run.  nvcc's split compile can come out in a 4-16 % slower code generation for identical sources (DESIGN.md,
+# "Build reproducibility"): `python -c "import __graft_entry__ as g; g.build(force=True)"` checks for it and recompiles.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 mkdir -p "$HERE/lib"
