@@ -26,6 +26,8 @@ def load():
     if _lib is None:
         lib = ctypes.CDLL(str(build()))
         lib.orc_num_threads.restype = c_int
+        lib.orc_set_num_threads.argtypes = [c_int]
+        lib.orc_encode_h84.argtypes = [c_void_p, c_void_p, c_int64]
         lib.orc_quantize_encode_h84.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p]
         lib.orc_xor_mask.argtypes = [c_void_p, c_void_p, c_void_p, c_int64]
         lib.orc_decode_h84.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
@@ -41,6 +43,19 @@ def _p(a: np.ndarray):
 
 def num_threads() -> int:
     return int(load().orc_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """Use `n` OpenMP threads from now on, whatever OMP_NUM_THREADS says; returns the count in effect."""
+    load().orc_set_num_threads(int(n))
+    return num_threads()
+
+
+def encode_h84(nib: np.ndarray, out: np.ndarray | None = None):
+    nib = np.ascontiguousarray(nib, dtype=np.uint8)
+    out = np.empty_like(nib) if out is None else out
+    load().orc_encode_h84(_p(nib), _p(out), nib.size)
+    return out
 
 
 def quantize_encode_h84(x: np.ndarray):

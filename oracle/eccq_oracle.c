@@ -66,6 +66,23 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* The thread count is set by the caller (bench.py passes the host's core count): OMP_NUM_THREADS, which torchrun sets to 1
+ * for its workers, must not decide how many cores the CPU baseline uses. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+/* flat Hamming(8,4) encode of nibbles (hamming84_triton.py:49-108), the first kernel of the config-1 round trip */
+void orc_encode_h84(const uint8_t* nib, uint8_t* cw, int64_t n) {
+  orc_init();
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) cw[i] = ENC84[nib[i] & 0x0F];
+}
+
 /* x [rows, D] fp32 -> codewords [rows, D] + scales [rows] */
 void orc_quantize_encode_h84(const float* x, int64_t rows, int D, uint8_t* cw, float* scales) {
   orc_init();

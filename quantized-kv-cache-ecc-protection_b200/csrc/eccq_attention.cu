@@ -9,20 +9,9 @@
 //
 // v0 (this file): CUDA-core dot products, warp per token.  The tcgen05/TMEM tile version builds on the same
 // partial/merge protocol.
-#include "eccq_internal.h"
+#include "eccq_attention.h"
 
 namespace eccq {
-
-struct AttnArgs {
-  const void* q;
-  void* out;
-  const int32_t* block_table;
-  const int32_t* context_lens;
-  float* ws;        // [nseq, Hq, nsplit, D + 2]  (acc[D], m, l)
-  int max_blocks, nseq, Hq, layer, nsplit, chunk;
-  float sm_scale;
-  int interp, v_use_k_scales, count_errors, force_general;
-};
 
 constexpr int kAttnThreads = 256;
 constexpr int kAttnWarps = kAttnThreads / 32;
@@ -304,12 +293,27 @@ static int dispatch_attn(const CacheGeom& g, const AttnArgs& a, uint64_t* counte
 }
 
 template <typename TQ>
-static int try_attn_mma(const CacheGeom& g, AttnArgs& a, uint64_t* counters, cudaStream_t st);  // eccq_attention_mma.cu (may coarsen a.chunk / a.nsplit)
+static int try_attn_mma(const CacheGeom& g, AttnArgs& a, uint64_t* counters, cudaStream_t st);  // eccq_attention_mma.cuh (may coarsen a.chunk / a.nsplit)
+
+template <typename TQ> struct DtypeCode;
+template <> struct DtypeCode<float> { static constexpr int value = ECCQ_F32; };
+template <> struct DtypeCode<__half> { static constexpr int value = ECCQ_F16; };
+template <> struct DtypeCode<__nv_bfloat16> { static constexpr int value = ECCQ_BF16; };
 
 template <typename TQ>
 static int run_attn(const CacheGeom& g, const AttnArgs& a_in, uint64_t* counters, cudaStream_t st) {
   AttnArgs a = a_in;
   int rc;
+  if (!a.force_general) {
+    // Blackwell-native tile kernel first (tcgen05 / TMEM / bulk TMA, eccq_attention_tc.cu); < 0 = launch error
+    const int took = try_attn_tc(g, a, DtypeCode<TQ>::value, counters, st);
+    if (took < 0) return took;
+    if (took) {
+      dim3 mg1(a.Hq, a.nseq);
+      attn_merge_kernel<TQ><<<mg1, 128, 0, st>>>(a.ws, reinterpret_cast<TQ*>(a.out), a.Hq, g.D, a.nsplit);
+      return ECCQ_OK;
+    }
+  }
   if (!a.force_general && try_attn_mma<TQ>(g, a, counters, st)) {
     dim3 mg0(a.Hq, a.nseq);
     attn_merge_kernel<TQ><<<mg0, 128, 0, st>>>(a.ws, reinterpret_cast<TQ*>(a.out), a.Hq, g.D, a.nsplit);
@@ -329,7 +333,11 @@ static int run_attn(const CacheGeom& g, const AttnArgs& a_in, uint64_t* counters
 
 }  // namespace eccq
 
+#include "eccq_attention_mma.cuh"
+
 using namespace eccq;
+
+ECCQ_DEFINE_TU_TABLES(attention)
 
 extern "C" int64_t eccq_attention_workspace_bytes(int nseq, int Hq, int D, int max_context) {
   if (nseq <= 0 || Hq <= 0 || D <= 0) return 0;

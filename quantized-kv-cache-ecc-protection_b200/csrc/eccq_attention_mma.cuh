@@ -1,4 +1,4 @@
-// eccq_attention_mma.cu -- ECC-fused paged decode attention, tensor-core tile version.
+// eccq_attention_mma.cuh -- ECC-fused paged decode attention, tensor-core tile version.
 //
 // One CTA = (sequence, kv-head, context chunk), four warps; each warp walks 16-token tiles (one tile never straddles a
 // page: block_size % 16 == 0).  Per tile:
@@ -18,7 +18,8 @@
 // tile loop around it, not by the tensor pipe.  Two prologues share this tile loop: SWAR (hamming_sel4, used when decode
 // errors are counted) and a shared-memory table (default, see attn_mma_kernel<..., LUT>).  Interpolation and Golay reach this
 // kernel through eccq_cache_correct_pages (corrected INT4 pages).  DESIGN.md 4.6 has the measurements and the tcgen05 note.
-#include "eccq_internal.h"
+#pragma once
+#include "eccq_attention.h"
 
 namespace eccq {
 

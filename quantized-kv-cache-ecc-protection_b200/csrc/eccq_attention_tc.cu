@@ -1,0 +1,608 @@
+// eccq_attention_tc.cu -- ECC-fused paged decode attention on the Blackwell tensor cores (tcgen05 + TMEM + bulk TMA).
+//
+// Replaces paged_attention_ecc_kernel (kv_cache/attention_ecc.py:264-426) for head_dim 128.  The cache stores one INT4
+// value per byte (a Hamming codeword whose corrected low nibble is the value), so after the syndrome decode a K or V page IS
+// an unsigned 8-bit matrix operand -- no float conversion of K/V ever happens:
+//
+//   S_int[128 tokens x 16]  = K[128 x 128 dims]  . Qd^T      tcgen05.mma kind::i8, A = decoded K tile (u8, K-major, 128B swizzle),
+//                                                            B = the GQA group's queries as 4 balanced base-128 digits (s8)
+//   O_int[128 dims x 16]    = V^T[128 x 128 tok] . Wb        A = decoded V tile (u8, MN-major: the SAME [token][dim] page image),
+//                                                            B = softmax weights p*v_scale as 32-bit fixed point, one byte per
+//                                                            column (u8, [token][16] rows written with one 16-byte store)
+//
+// Both products are EXACT integer arithmetic (int32 accumulators in TMEM); the only roundings are the 28-bit query / 32-bit
+// weight quantisation, far below the fp32 rounding of the reference's dot products.  The "-8" of (nibble - 8) is folded into
+// per-head constants (QK^T) and into the running sum of weights (PV).
+//
+// One persistent CTA per SM, warp-specialised, all hand-offs through mbarriers:
+//   warp 0      producer: walks the block table, one cp.async.bulk (TMA) per K page, V page and scale row into a ring of
+//               128-token stages (complete_tx on the stage's "full" barrier)
+//   warp 1      MMA issuer (one thread): 4 + 4 tcgen05.mma per tile, tcgen05.commit to the barriers that hand S / O to the
+//               softmax warps and the stage back to the producer
+//   warp 2      query preparation for the next (sequence, kv-head, split) item: digits + constants, double buffered
+//   warp 3      TMEM allocation
+//   warps 4-7   softmax: thread = token (TMEM lane) for S, thread = dim for O; online softmax in base 2, fp32 state
+//   warps 8..   decode: LDS.128 raw codewords -> SWAR syndrome decode (eccq_common.cuh) -> STS.128 corrected nibbles IN PLACE
+//               at the 128-byte-swizzled position the UMMA descriptors expect
+// Partials (acc[D], m, l) per split go through the same workspace / attn_merge_kernel as the other attention kernels.
+#include "eccq_attention.h"
+
+namespace eccq {
+namespace tc {
+
+constexpr int kTile = 128;                 // tokens per tile (= M of QK^T, K of PV)
+constexpr int kD = 128;                    // head_dim served by this kernel
+constexpr int kStages = 5;
+constexpr int kPartBytes = kTile * kD;     // one K or V tile: 16 KB
+constexpr int kStageBytes = 2 * kPartBytes + 2 * kTile * 4;   // K, V, k scales, v scales = 33 KB (multiple of 1024)
+constexpr int kQopBytes = 16 * 128;        // 16 digit rows x 128 dims
+constexpr int kWBytes = kTile * 16;        // [token][16 weight bytes]
+constexpr int kFrontWarps = 8;             // producer, mma, query, tmem + 4 softmax
+constexpr int kHeadsPerPass = 4;           // q-heads per item: 4 heads x 4 digits = N 16
+constexpr uint32_t kSpinLimit = 1u << 26;
+
+// ---- shared-memory map (offsets from a 1024-byte aligned base) -------------------------------------------------------
+constexpr int kOffStages = 0;
+constexpr int kOffQop = kOffStages + kStages * kStageBytes;
+constexpr int kOffW = kOffQop + 2 * kQopBytes;
+constexpr int kOffMisc = kOffW + 2 * kWBytes;
+struct Misc {
+  uint64_t full[kStages], kdec[kStages], vdec[kStages], empty[kStages];
+  uint64_t sready[2], wready[2], oready[2], qready[2], qfree[2];
+  float qscale[2][kHeadsPerPass];        // 2^(e-27) * sm_scale * log2(e) per head (0 for unused heads)
+  int32_t qc01[2][kHeadsPerPass];        // 8 * sum_d (d0*128 + d1)
+  int32_t qc23[2][kHeadsPerPass];        // 8 * sum_d (d2*128 + d3)
+  float red[2][4][8];                    // per-tile exchange of the softmax warps: max score per head, max v scale
+  float fin[4][8];                       // end-of-item reduction: l and sum(w) per head per warp
+  uint32_t page_mask[kStages];           // bit j: page j of the stage's tile was loaded
+  uint32_t tmem_base;
+};
+constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc) + 1024;   // + alignment slack
+
+struct Args {
+  CacheGeom g;
+  const void* q;
+  int q_dtype;
+  const int32_t* block_table;
+  const int32_t* context_lens;
+  float* ws;
+  const float* vscales;
+  int max_blocks, nseq, Hq, layer, nsplit, chunk, npass, count_errors;
+  float sm_scale;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(b)), "r"(bytes) : "memory"); }
+// every wait is bounded: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  const uint32_t a = sptr(b);
+  for (uint32_t it = 0; it < kSpinLimit; ++it) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sptr(dst)), "l"(src), "r"(bytes), "r"(sptr(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* b) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sptr(b)) : "memory"); }
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{ .reg .pred p; setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p; }" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 @0, LBO >> 4 @16, SBO >> 4 @32, version 1 @46,
+// layout type @61 (0 = no swizzle, 2 = 128-byte swizzle)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+         ((uint64_t)layout << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 @4, a/b signedness @7/@10, a/b major @15/@16, N>>3 @17, M>>4 @24
+constexpr uint32_t kIdescS = (2u << 4) | (0u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);   // u8 x s8, K-major both
+constexpr uint32_t kIdescO = (2u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((128u >> 4) << 24);   // u8 x u8, MN-major both
+
+// ---- work items ---------------------------------------------------------------------------------------------------------
+struct Item {
+  int seq, kvh, pass, split, c0, c1, tile0, ntiles;
+};
+__device__ __forceinline__ bool get_item(const Args& a, int item, Item& it) {
+  it.split = item % a.nsplit;
+  int r = item / a.nsplit;
+  it.pass = r % a.npass;
+  r /= a.npass;
+  it.kvh = r % a.g.H;
+  it.seq = r / a.g.H;
+  const int ctx = min(a.context_lens[it.seq], a.max_blocks * a.g.bs);
+  it.c0 = it.split * a.chunk;
+  it.c1 = min(ctx, it.c0 + a.chunk);
+  it.tile0 = it.c0 / kTile;
+  it.ntiles = it.c1 > it.c0 ? (it.c1 - it.c0 + kTile - 1) / kTile : 0;
+  return it.ntiles > 0;
+}
+
+__device__ __forceinline__ float load_q(const void* q, int dtype, int64_t i) {
+  if (dtype == ECCQ_F32) return reinterpret_cast<const float*>(q)[i];
+  if (dtype == ECCQ_F16) return __half2float(reinterpret_cast<const __half*>(q)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(q)[i]);
+}
+
+template <int CODEC, bool COUNT>
+__device__ __forceinline__ uint32_t decode_nibbles(uint32_t w, FlagCount& fc, bool counted) {
+  if (CODEC == ECCQ_CODEC_H84 || CODEC == ECCQ_CODEC_H74) {
+    constexpr int HC = CODEC == ECCQ_CODEC_H74 ? ECCQ_CODEC_H74 : ECCQ_CODEC_H84;
+    const uint32_t sel = hamming_sel4<HC>(w);
+    if (COUNT) fc.add(counted ? prmt(kFlagLutLo, kFlagLutHi, sel) : 0u);
+    return lop3<kLopXorAnd>(w, prmt(kFlipLutLo, kFlipLutHi, sel), M0F);
+  }
+  return w & M0F;
+}
+
+template <int CODEC, bool COUNT, int NDEC>
+__global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(const Args a, uint64_t* counters) {
+  extern __shared__ __align__(16) unsigned char eccq_tc_smem[];
+  const uint32_t raw = sptr(eccq_tc_smem);
+  unsigned char* const sm = eccq_tc_smem + ((1024u - (raw & 1023u)) & 1023u);
+  Misc& mi = *reinterpret_cast<Misc*>(sm + kOffMisc);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bs = a.g.bs;
+  const int ppt = kTile / bs;                       // pages per tile
+  const int nitems = a.nseq * a.g.H * a.npass * a.nsplit;
+  const int G = a.Hq / a.g.H;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&mi.full[s], 1);
+      mbar_init(&mi.kdec[s], NDEC);
+      mbar_init(&mi.vdec[s], NDEC);
+      mbar_init(&mi.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&mi.sready[b], 1);
+      mbar_init(&mi.wready[b], 128);
+      mbar_init(&mi.oready[b], 1);
+      mbar_init(&mi.qready[b], 1);
+      mbar_init(&mi.qfree[b], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 3) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(sptr(&mi.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_before();
+  __syncthreads();
+  tc_after();
+  const uint32_t tmem = mi.tmem_base;   // columns [0,32): S buffers, [32,64): O buffers
+
+  if (warp == 0) {
+    // =============================================================== producer
+    const uint32_t page_tx = (uint32_t)(2 * bs * kD + 2 * bs * 4);
+    int n = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      Item it;
+      if (!get_item(a, item, it)) continue;
+      const int32_t* bt = a.block_table + (int64_t)it.seq * a.max_blocks;
+      for (int t = 0; t < it.ntiles; ++t, ++n) {
+        const int s = n % kStages;
+        if (lane == 0) mbar_wait(&mi.empty[s], ((n / kStages) & 1) ^ 1);
+        __syncwarp();
+        const int tok0 = (it.tile0 + t) * kTile + lane * bs;
+        const int lb = tok0 / bs;
+        int blk = -1;
+        if (lane < ppt && tok0 < it.c1 && lb < a.max_blocks) blk = bt[lb];
+        const uint32_t vm = __ballot_sync(0xFFFFFFFFu, blk >= 0);
+        unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
+        if (lane == 0) {
+          mi.page_mask[s] = vm;
+          mbar_arrive_tx(&mi.full[s], (uint32_t)__popc(vm) * page_tx);
+        }
+        if (blk >= 0) {
+          const int64_t page = page_index(a.g, blk, a.layer, it.kvh);
+          bulk_g2s(st + lane * bs * kD, a.g.k_cache + page * (int64_t)(bs * kD), (uint32_t)(bs * kD), &mi.full[s]);
+          bulk_g2s(st + kPartBytes + lane * bs * kD, a.g.v_cache + page * (int64_t)(bs * kD), (uint32_t)(bs * kD), &mi.full[s]);
+          bulk_g2s(st + 2 * kPartBytes + lane * bs * 4, a.g.k_scales + page * bs, (uint32_t)(bs * 4), &mi.full[s]);
+          bulk_g2s(st + 2 * kPartBytes + kTile * 4 + lane * bs * 4, a.vscales + page * bs, (uint32_t)(bs * 4), &mi.full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      struct Cur { int item, t, n, j, ntiles; bool valid; };
+      auto seek = [&](Cur& c) {   // c.item points at a candidate: skip empty items
+        Item it;
+        while (c.item < nitems && !get_item(a, c.item, it)) c.item += gridDim.x;
+        c.valid = c.item < nitems;
+        if (c.valid) c.ntiles = it.ntiles;
+      };
+      auto advance = [&](Cur& c) {
+        ++c.n;
+        if (++c.t == c.ntiles) { c.t = 0; ++c.j; c.item += gridDim.x; seek(c); }
+      };
+      auto issue_s = [&](const Cur& c) {
+        const int s = c.n % kStages, b = c.n & 1, qb = c.j & 1;
+        if (c.t == 0) mbar_wait(&mi.qready[qb], (c.j >> 1) & 1);
+        mbar_wait(&mi.kdec[s], (c.n / kStages) & 1);
+        tc_after();
+        const uint32_t ka = sptr(sm + kOffStages + (size_t)s * kStageBytes), qa = sptr(sm + kOffQop + qb * kQopBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_i8(tmem + b * 16, smem_desc(ka + k * 32, 16, 1024, 2), smem_desc(qa + k * 32, 16, 1024, 2), kIdescS, k > 0);
+        tc_commit(&mi.sready[b]);
+      };
+      auto issue_pv = [&](const Cur& c) {
+        const int s = c.n % kStages, b = c.n & 1;
+        mbar_wait(&mi.wready[b], (c.n >> 1) & 1);
+        mbar_wait(&mi.vdec[s], (c.n / kStages) & 1);
+        tc_after();
+        const uint32_t va = sptr(sm + kOffStages + (size_t)s * kStageBytes + kPartBytes), wa = sptr(sm + kOffW + b * kWBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_i8(tmem + 32 + b * 16, smem_desc(va + k * 4096, 16, 1024, 2), smem_desc(wa + k * 512, 128, 256, 0), kIdescO, k > 0);
+        tc_commit(&mi.oready[b]);
+        tc_commit(&mi.empty[s]);
+      };
+      Cur cs{(int)blockIdx.x, 0, 0, 0, 0, false}, cp;
+      seek(cs);
+      cp = cs;
+      if (cs.valid) { issue_s(cs); advance(cs); }
+      while (cp.valid) {
+        if (cs.valid) { issue_s(cs); advance(cs); }
+        issue_pv(cp);
+        advance(cp);
+      }
+    }
+  } else if (warp == 2) {
+    // =============================================================== query digits for the next item
+    int j = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      Item it;
+      if (!get_item(a, item, it)) continue;
+      const int qb = j & 1;
+      mbar_wait(&mi.qfree[qb], ((j >> 1) & 1) ^ 1);
+      const int hh = lane >> 3, c = lane & 7;               // head of the pass, 16-dim chunk
+      const int g0 = it.pass * kHeadsPerPass;
+      const bool used = g0 + hh < G;
+      float v[16];
+      float amax = 0.0f;
+      const int64_t qbase = ((int64_t)it.seq * a.Hq + (int64_t)it.kvh * G + g0 + hh) * kD + c * 16;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        v[e] = used ? load_q(a.q, a.q_dtype, qbase + e) : 0.0f;
+        amax = fmaxf(amax, fabsf(v[e]));
+      }
+      amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 1));
+      amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 2));
+      amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 4));
+      // amax = m * 2^ex with m in [0.5, 1): |q| * 2^(27-ex) < 2^27
+      int ex = 0;
+      if (amax > 0.0f && amax < INFINITY) (void)frexpf(amax, &ex);
+      const float up = ldexpf(1.0f, 27 - ex);
+      uint32_t dig[4][4];   // [digit][word of 4 dims]
+      int32_t s01 = 0, s23 = 0;
+#pragma unroll
+      for (int w4 = 0; w4 < 4; ++w4) {
+        uint32_t pk[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int32_t x = __float2int_rn(v[w4 * 4 + e] * up);
+          const int32_t d3 = ((x + 64) & 127) - 64; x = (x - d3) >> 7;
+          const int32_t d2 = ((x + 64) & 127) - 64; x = (x - d2) >> 7;
+          const int32_t d1 = ((x + 64) & 127) - 64; x = (x - d1) >> 7;
+          const int32_t d0 = x;
+          s01 += d0 * 128 + d1;
+          s23 += d2 * 128 + d3;
+          pk[0] |= (uint32_t)(d0 & 0xFF) << (8 * e);
+          pk[1] |= (uint32_t)(d1 & 0xFF) << (8 * e);
+          pk[2] |= (uint32_t)(d2 & 0xFF) << (8 * e);
+          pk[3] |= (uint32_t)(d3 & 0xFF) << (8 * e);
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) dig[l][w4] = pk[l];
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        s01 += __shfl_xor_sync(0xFFFFFFFFu, s01, o);
+        s23 += __shfl_xor_sync(0xFFFFFFFFu, s23, o);
+      }
+      unsigned char* qop = sm + kOffQop + qb * kQopBytes;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int row = hh * 4 + l;
+        *reinterpret_cast<uint4*>(qop + row * 128 + ((c ^ (row & 7)) << 4)) = make_uint4(dig[l][0], dig[l][1], dig[l][2], dig[l][3]);
+      }
+      if (c == 0) {
+        mi.qscale[qb][hh] = used ? ldexpf(a.sm_scale * 1.4426950408889634f, ex - 27) : 0.0f;
+        mi.qc01[qb][hh] = 8 * s01;
+        mi.qc23[qb][hh] = 8 * s23;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&mi.qready[qb]);
+      ++j;
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // =============================================================== softmax / accumulate
+    const int w = warp - 4;
+    const int r = w * 32 + lane;                       // token row of S, dim row of O
+    const uint32_t tlane = (uint32_t)(w * 32) << 16;
+    int n = 0, j = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      Item it;
+      const bool live = get_item(a, item, it);
+      const int g0 = it.pass * kHeadsPerPass;
+      const int ng = min(kHeadsPerPass, G - g0);
+      if (!live) {   // empty split: neutral partial
+        for (int gi = 0; gi < ng; ++gi) {
+          float* wsrow = a.ws + (((int64_t)it.seq * a.Hq + it.kvh * G + g0 + gi) * a.nsplit + it.split) * (kD + 2);
+          wsrow[r] = 0.0f;
+          if (r == 0) { wsrow[kD] = -INFINITY; wsrow[kD + 1] = 0.0f; }
+        }
+        continue;
+      }
+      const int qb = j & 1;
+      mbar_wait(&mi.qready[qb], (j >> 1) & 1);
+      float qs[4]; int32_t c01[4], c23[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) { qs[h] = mi.qscale[qb][h]; c01[h] = mi.qc01[qb][h]; c23[h] = mi.qc23[qb][h]; }
+      float m_run[4], l_thr[4], lw_thr[4], oacc[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) { m_run[h] = -INFINITY; l_thr[h] = 0.0f; lw_thr[h] = 0.0f; oacc[h] = 0.0f; }
+      float sigma_prev = 0.0f;
+      auto drain_o = [&](int nn, const float (&scale)[4]) {   // O of tile nn (buffer nn & 1) -> oacc
+        const int b = nn & 1;
+        mbar_wait(&mi.oready[b], (nn >> 1) & 1);
+        tc_after();
+        uint32_t o[16];
+        tmem_ld16(tmem + 32 + b * 16 + tlane, o);
+        tc_before();
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float v = __int2float_rn((int32_t)o[4 * h + 3]);
+          v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * h + 2]));
+          v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * h + 1]));
+          v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * h]));
+          oacc[h] = fmaf(v, scale[h], oacc[h]);
+        }
+      };
+      for (int t = 0; t < it.ntiles; ++t, ++n) {
+        const int s = n % kStages, b = n & 1;
+        const unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
+        mbar_wait(&mi.full[s], (n / kStages) & 1);
+        const int tok = (it.tile0 + t) * kTile + r;
+        const bool valid = tok < it.c1 && ((mi.page_mask[s] >> (r / bs)) & 1u);
+        const float ks = reinterpret_cast<const float*>(st + 2 * kPartBytes)[r];
+        const float vs = valid ? reinterpret_cast<const float*>(st + 2 * kPartBytes + kTile * 4)[r] : 0.0f;
+        mbar_wait(&mi.sready[b], (n >> 1) & 1);
+        tc_after();
+        uint32_t sr[16];
+        tmem_ld16(tmem + b * 16 + tlane, sr);
+        tc_before();
+        float sc[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int32_t hi = (int32_t)sr[4 * h] * 128 + (int32_t)sr[4 * h + 1] - c01[h];
+          const int32_t lo = (int32_t)sr[4 * h + 2] * 128 + (int32_t)sr[4 * h + 3] - c23[h];
+          const float f = fmaf(__int2float_rn(hi), 16384.0f, __int2float_rn(lo));
+          sc[h] = valid ? f * (ks * qs[h]) : -INFINITY;
+        }
+        // ---- tile maxima: warp redux, then the four warps exchange through shared memory
+        {
+          float wm[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) wm[h] = warp_max_f32(sc[h]);
+          const float wv = warp_max_f32(vs);
+          if (lane == 0) {
+            *reinterpret_cast<float4*>(&mi.red[b][w][0]) = make_float4(wm[0], wm[1], wm[2], wm[3]);
+            mi.red[b][w][4] = wv;
+          }
+        }
+        named_bar_sync(1, 128);
+        float alpha[4], vsmax = 0.0f;
+#pragma unroll
+        for (int ww = 0; ww < 4; ++ww) {
+          const float4 x = *reinterpret_cast<const float4*>(&mi.red[b][ww][0]);
+          if (ww == 0) { alpha[0] = x.x; alpha[1] = x.y; alpha[2] = x.z; alpha[3] = x.w; }
+          else { alpha[0] = fmaxf(alpha[0], x.x); alpha[1] = fmaxf(alpha[1], x.y); alpha[2] = fmaxf(alpha[2], x.z); alpha[3] = fmaxf(alpha[3], x.w); }
+          vsmax = fmaxf(vsmax, mi.red[b][ww][4]);
+        }
+        // weights as 32-bit fixed point relative to 2^E > vsmax: wscale = 2^(32-E), sigma = 2^(E-32)
+        const uint32_t eb = min(max(__float_as_uint(vsmax) >> 23, 32u), 254u);
+        const float wscale = __uint_as_float((285u - eb) << 23);
+        const float sigma = __uint_as_float((eb - 31u) << 23);
+        uint32_t wfix[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float mn = fmaxf(m_run[h], alpha[h]);           // alpha[] holds the tile maximum here
+          const float al = (mn == -INFINITY) ? 1.0f : exp2f(m_run[h] - mn);
+          const float p = (sc[h] == -INFINITY) ? 0.0f : exp2f(sc[h] - mn);
+          const float pw = p * vs;
+          m_run[h] = mn;
+          alpha[h] = al;
+          l_thr[h] = fmaf(l_thr[h], al, p);
+          lw_thr[h] = fmaf(lw_thr[h], al, pw);
+          oacc[h] *= al;
+          wfix[h] = __float2uint_rn(pw * wscale);
+        }
+        *reinterpret_cast<uint4*>(sm + kOffW + b * kWBytes + r * 16) = make_uint4(wfix[0], wfix[1], wfix[2], wfix[3]);
+        fence_async_smem();
+        mbar_arrive(&mi.wready[b]);
+        // ---- previous tile's O (relative to the previous running maximum): rescale by this tile's alpha
+        if (t > 0) {
+          const float sca[4] = {sigma_prev * alpha[0], sigma_prev * alpha[1], sigma_prev * alpha[2], sigma_prev * alpha[3]};
+          drain_o(n - 1, sca);
+        }
+        sigma_prev = sigma;
+      }
+      {
+        const float sca[4] = {sigma_prev, sigma_prev, sigma_prev, sigma_prev};
+        drain_o(n - 1, sca);
+      }
+      // ---- end of item: sums over the 128 token threads, write the partial
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          l_thr[h] += __shfl_xor_sync(0xFFFFFFFFu, l_thr[h], o);
+          lw_thr[h] += __shfl_xor_sync(0xFFFFFFFFu, lw_thr[h], o);
+        }
+      if (lane == 0) {
+        *reinterpret_cast<float4*>(&mi.fin[w][0]) = make_float4(l_thr[0], l_thr[1], l_thr[2], l_thr[3]);
+        *reinterpret_cast<float4*>(&mi.fin[w][4]) = make_float4(lw_thr[0], lw_thr[1], lw_thr[2], lw_thr[3]);
+      }
+      named_bar_sync(1, 128);
+      float L[4] = {0, 0, 0, 0}, LW[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int ww = 0; ww < 4; ++ww) {
+        const float4 x = *reinterpret_cast<const float4*>(&mi.fin[ww][0]);
+        const float4 y = *reinterpret_cast<const float4*>(&mi.fin[ww][4]);
+        L[0] += x.x; L[1] += x.y; L[2] += x.z; L[3] += x.w;
+        LW[0] += y.x; LW[1] += y.y; LW[2] += y.z; LW[3] += y.w;
+      }
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        if (h < ng) {
+          float* wsrow = a.ws + (((int64_t)it.seq * a.Hq + it.kvh * G + g0 + h) * a.nsplit + it.split) * (kD + 2);
+          wsrow[r] = fmaf(-8.0f, LW[h], oacc[h]);
+          // the merge kernel works in natural-log units
+          if (r == 0) { wsrow[kD] = (m_run[h] == -INFINITY) ? -INFINITY : m_run[h] * 0.6931471805599453f; wsrow[kD + 1] = L[h]; }
+        }
+      }
+      named_bar_sync(1, 128);          // mi.fin is reused by the next item
+      mbar_arrive(&mi.qfree[qb]);
+      ++j;
+    }
+  } else if (warp >= kFrontWarps) {
+    // =============================================================== decode, in place
+    const int dw = warp - kFrontWarps;
+    constexpr int OPS = 32 / NDEC > 0 ? 32 / NDEC : 1;   // warp-wide 512-byte operations per part (K or V) per warp
+    static_assert(32 % NDEC == 0, "decode warps must divide the 32 row groups of a part");
+    FlagCount fc;
+    int n = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      Item it;
+      if (!get_item(a, item, it)) continue;
+      const bool do_count = COUNT && it.pass == 0;
+      for (int t = 0; t < it.ntiles; ++t, ++n) {
+        const int s = n % kStages;
+        unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
+        mbar_wait(&mi.full[s], (n / kStages) & 1);
+        const uint32_t pm = COUNT ? mi.page_mask[s] : 0u;
+        const int tokbase = (it.tile0 + t) * kTile;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          uint4 x[OPS];
+          uint32_t wr[OPS];
+          bool cnt[OPS];
+#pragma unroll
+          for (int i = 0; i < OPS; ++i) {
+            const int row = (dw + i * NDEC) * 4 + (lane >> 3), c = lane & 7;
+            const uint32_t base = sptr(st + part * kPartBytes + row * 128);
+            wr[i] = base + (uint32_t)((c ^ (row & 7)) << 4);
+            cnt[i] = do_count && tokbase + row < it.c1 && ((pm >> (row / bs)) & 1u);
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x[i].x), "=r"(x[i].y), "=r"(x[i].z), "=r"(x[i].w) : "r"(base + (uint32_t)(c << 4)));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < OPS; ++i) {
+            const uint32_t y0 = decode_nibbles<CODEC, COUNT>(x[i].x, fc, cnt[i]);
+            const uint32_t y1 = decode_nibbles<CODEC, COUNT>(x[i].y, fc, cnt[i]);
+            const uint32_t y2 = decode_nibbles<CODEC, COUNT>(x[i].z, fc, cnt[i]);
+            const uint32_t y3 = decode_nibbles<CODEC, COUNT>(x[i].w, fc, cnt[i]);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wr[i]), "r"(y0), "r"(y1), "r"(y2), "r"(y3) : "memory");
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(part == 0 ? &mi.kdec[s] : &mi.vdec[s]);
+        }
+      }
+    }
+    if (COUNT) {
+      const uint32_t ns = __reduce_add_sync(0xFFFFFFFFu, fc.singles()), nd = __reduce_add_sync(0xFFFFFFFFu, fc.doubles());
+      if (lane == 0 && counters != nullptr) {
+        if (ns) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + ECCQ_CTR_CORRECTED, (unsigned long long)ns);
+        if (nd) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + ECCQ_CTR_DETECTED, (unsigned long long)nd);
+      }
+    }
+  }
+  tc_before();
+  __syncthreads();
+  if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
+}
+
+template <int CODEC, bool COUNT, int NDEC>
+static int launch(const Args& a, uint64_t* counters, cudaStream_t st) {
+  auto kern = attn_tc_kernel<CODEC, COUNT, NDEC>;
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);   // per device
+  if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
+  const int nitems = a.nseq * a.g.H * a.npass * a.nsplit;
+  kern<<<std::min(nitems, sm_count()), (kFrontWarps + NDEC) * 32, kSmemBytes, st>>>(a, counters);
+  return check_launch("paged_decode_attention (tcgen05)");
+}
+
+}  // namespace tc
+
+// returns 1 when the tcgen05 kernel took the launch (partials written; the caller runs the merge), 0 when the geometry is
+// outside it, < 0 on error.  May lower a.nsplit / raise a.chunk (fewer, longer splits; the workspace was sized for more).
+int try_attn_tc(const CacheGeom& g, AttnArgs& a, int q_dtype, uint64_t* counters, cudaStream_t st) {
+  static const int env = [] { const char* v = std::getenv("ECCQ_ATTN_TC"); return v && *v ? std::atoi(v) : 1; }();
+  if (!env || g.codec == ECCQ_CODEC_GOLAY || a.interp || g.D != tc::kD) return 0;
+  if (g.bs < 16 || g.bs > tc::kTile || (tc::kTile % g.bs) != 0) return 0;
+  if (!aligned16(g.k_cache) || !aligned16(g.v_cache) || !aligned16(g.k_scales) || !aligned16(g.v_scales)) return 0;
+  const int G = a.Hq / g.H;
+  tc::Args t;
+  t.g = g; t.q = a.q; t.q_dtype = q_dtype; t.block_table = a.block_table; t.context_lens = a.context_lens; t.ws = a.ws;
+  t.vscales = a.v_use_k_scales ? g.k_scales : g.v_scales;
+  t.max_blocks = a.max_blocks; t.nseq = a.nseq; t.Hq = a.Hq; t.layer = a.layer; t.sm_scale = a.sm_scale;
+  t.npass = (G + tc::kHeadsPerPass - 1) / tc::kHeadsPerPass;
+  t.count_errors = a.count_errors;
+  // splits: multiples of the 128-token tile, at least 2048 tokens, never more splits than the workspace was planned for
+  const int64_t maxctx = (int64_t)a.max_blocks * g.bs;
+  int chunk = (int)(((maxctx + a.nsplit - 1) / a.nsplit + tc::kTile - 1) / tc::kTile * tc::kTile);
+  static const int min_chunk = [] { const char* v = std::getenv("ECCQ_ATTN_TC_CHUNK"); return v && *v ? std::atoi(v) : 2048; }();
+  chunk = std::max(chunk, std::max(min_chunk / tc::kTile * tc::kTile, tc::kTile));
+  a.chunk = chunk;
+  a.nsplit = (int)((maxctx + chunk - 1) / chunk);
+  t.chunk = a.chunk; t.nsplit = a.nsplit;
+  static const int ndec = [] { const char* v = std::getenv("ECCQ_ATTN_TC_NDEC"); return v && *v ? std::atoi(v) : 16; }();
+  int rc;
+#define ECCQ_TC_CASE(C, CNT)                                            \
+  rc = ndec == 8 ? tc::launch<C, CNT, 8>(t, counters, st) : tc::launch<C, CNT, 16>(t, counters, st)
+  if (a.count_errors) {
+    switch (g.codec) {
+      case ECCQ_CODEC_H84: ECCQ_TC_CASE(ECCQ_CODEC_H84, true); break;
+      case ECCQ_CODEC_H74: ECCQ_TC_CASE(ECCQ_CODEC_H74, true); break;
+      default: ECCQ_TC_CASE(ECCQ_CODEC_INT4, false); break;
+    }
+  } else {
+    switch (g.codec) {
+      case ECCQ_CODEC_H84: ECCQ_TC_CASE(ECCQ_CODEC_H84, false); break;
+      case ECCQ_CODEC_H74: ECCQ_TC_CASE(ECCQ_CODEC_H74, false); break;
+      default: ECCQ_TC_CASE(ECCQ_CODEC_INT4, false); break;
+    }
+  }
+#undef ECCQ_TC_CASE
+  return rc ? rc : 1;
+}
+
+}  // namespace eccq

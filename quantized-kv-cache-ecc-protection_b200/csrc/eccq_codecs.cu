@@ -479,6 +479,8 @@ static inline int grid_for(int64_t work_items, int per_block) {
 
 using namespace eccq;
 
+ECCQ_DEFINE_TU_TABLES(codecs)
+
 extern "C" int eccq_h74_encode(const uint8_t* in, uint8_t* out, int64_t n, void* stream) {
   if (n < 0 || (n && (!in || !out))) return fail(ECCQ_EINVAL, "h74_encode: bad arguments");
   if (n == 0) return ECCQ_OK;

@@ -229,8 +229,9 @@ struct GolayTables {
   uint16_t par_hi[64];
   int32_t syn[4096];  // config.py:403-457; -1 = uncorrectable
 };
-// Single translation unit (eccq_lib.cu), so the symbol is defined here; filled once per device by ensure_tables().
-__device__ GolayTables g_golay;
+// No relocatable device code: every translation unit that reads the tables owns a copy of the symbol and registers an
+// uploader (ECCQ_DEFINE_TU_TABLES, eccq_internal.h); ensure_tables() fills all copies once per device.
+static __device__ GolayTables g_golay;
 
 __device__ __forceinline__ uint32_t golay_parity(const uint16_t* lo, const uint16_t* hi, uint32_t d) {
   return (uint32_t)lo[d & 63u] ^ (uint32_t)hi[(d >> 6) & 63u];

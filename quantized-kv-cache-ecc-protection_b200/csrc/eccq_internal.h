@@ -1,4 +1,4 @@
-// eccq_internal.h -- host-side helpers of the single translation unit eccq_lib.cu (error reporting, device info,
+// eccq_internal.h -- host-side helpers shared by the translation units of libeccq_sm100a.so (error reporting, device info,
 // one-time per-device upload of the Golay tables).
 #pragma once
 #include <algorithm>
@@ -117,7 +117,16 @@ inline void build_byte_table(uint8_t* t, bool h84) {
 }
 const uint16_t* ensure_pair_tables();   // device pointer to the two 256-byte tables [H74][H84]; defined in eccq_lib.cu
 
-int ensure_tables();  // defined in eccq_lib.cu next to the __device__ symbol
+int ensure_tables();  // defined in eccq_lib.cu: uploads the Golay tables into every translation unit's copy, once per device
+
+// A translation unit that reads g_golay (eccq_common.cuh) registers an uploader for ITS copy of the symbol.
+using TableUploader = cudaError_t (*)(const GolayTables&);
+void register_table_uploader(TableUploader f);   // eccq_lib.cu
+#define ECCQ_DEFINE_TU_TABLES(name)                                                                                      \
+  static cudaError_t eccq_upload_tables_##name(const eccq::GolayTables& t) {                                             \
+    return cudaMemcpyToSymbol(eccq::g_golay, &t, sizeof(eccq::GolayTables), 0, cudaMemcpyHostToDevice);                  \
+  }                                                                                                                      \
+  static const int eccq_tables_registered_##name = (eccq::register_table_uploader(&eccq_upload_tables_##name), 0);
 
 inline FastInject make_fast_inject(float ber, uint64_t seed) {
   FastInject fi;

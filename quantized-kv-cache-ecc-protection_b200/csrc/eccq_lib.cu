@@ -1,10 +1,17 @@
-// eccq_lib.cu -- the single translation unit of libeccq_sm100a.so (unity build: the kernels share one __device__
-// table symbol and are compiled for sm_100a only; no relocatable device code, no other architectures).
+// eccq_lib.cu -- library-level state of libeccq_sm100a.so: table upload, device info, error string.  The kernels live in
+// their own translation units (codecs, cache write, cache read, attention, tcgen05 attention), compiled in parallel for
+// sm_100a only, without relocatable device code.
 #include "eccq_internal.h"
 
 namespace eccq {
 
 static std::mutex g_mu;
+
+static std::vector<TableUploader>& uploaders() {
+  static std::vector<TableUploader> v;
+  return v;
+}
+void register_table_uploader(TableUploader f) { uploaders().push_back(f); }
 
 int ensure_tables() {
   DeviceState& s = device_state();
@@ -13,8 +20,10 @@ int ensure_tables() {
   if (s.tables) return ECCQ_OK;
   const GolayTables& t = host_golay_tables();
   // synchronous on purpose: happens once per device, before the first kernel that needs the tables
-  const cudaError_t e = cudaMemcpyToSymbol(g_golay, &t, sizeof(GolayTables), 0, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
+  for (TableUploader up : uploaders()) {
+    const cudaError_t e = up(t);
+    if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
+  }
   s.tables = true;
   return ECCQ_OK;
 }
@@ -36,11 +45,6 @@ const uint16_t* ensure_pair_tables() {
 }
 
 }  // namespace eccq
-
-#include "eccq_codecs.cu"
-#include "eccq_cache.cu"
-#include "eccq_attention.cu"
-#include "eccq_attention_mma.cu"
 
 extern "C" int eccq_abi_version(void) { return ECCQ_ABI_VERSION; }
 extern "C" const char* eccq_last_error(void) { return eccq::last_error_ref(); }

@@ -285,15 +285,26 @@ class ECCBackend:
         dt = q.dtype if q.dtype in (torch.float32, torch.float16, torch.bfloat16) else torch.float32
         k, v = read_cache(m.k_cache, m.v_cache, m.k_scales, m.v_scales, bt, cl, layer_idx, m.block_size, D, cfg.codec,
                           use_interpolation=cfg.use_interpolation, out_dtype=dt, counters=self._counters, max_context=max(lens))
-        return self._run_attention(q, k, v)
+        mask = None
+        if cfg.append and (min(lens) != max(lens) or lens[0] != Sq):
+            # chunked prefill / ragged batch: query t of row b sits at position lens[b]-Sq+t and sees keys <= that position
+            # (bottom-right aligned causal mask; it also hides the zero padding past a shorter sequence).  SDPA's
+            # is_causal is top-left aligned and is only right for a one-shot prefill of equal lengths.
+            key_pos = torch.arange(k.shape[1], device=q.device)
+            q_pos = cl.to(torch.int64)[:, None] - Sq + torch.arange(Sq, device=q.device)[None, :]
+            mask = (key_pos[None, None, :] <= q_pos[:, :, None])[:, None]          # [B, 1, Sq, ctx]
+        return self._run_attention(q, k, v, mask)
 
-    def _run_attention(self, q, k, v):
+    def _run_attention(self, q, k, v, attn_mask=None):
         """ecc_shim.py:1138-1164: GQA expand + SDPA, causal (top-left) when q_len > 1. k, v: [nseq, ctx, Hkv, D]."""
         k = k.permute(0, 2, 1, 3)
         v = v.permute(0, 2, 1, 3)
         if k.shape[0] != q.shape[0]:
             k, v = k.expand(q.shape[0], -1, -1, -1), v.expand(q.shape[0], -1, -1, -1)
         # the GQA expansion happens inside SDPA (no Hq-sized copy of K/V, which the reference makes with repeat_interleave)
+        if attn_mask is not None:
+            return F.scaled_dot_product_attention(q, k.to(q.dtype), v.to(q.dtype), attn_mask=attn_mask,
+                                                  enable_gqa=self.num_kv_groups > 1)
         return F.scaled_dot_product_attention(q, k.to(q.dtype), v.to(q.dtype), is_causal=q.shape[2] > 1,
                                               enable_gqa=self.num_kv_groups > 1)
 
