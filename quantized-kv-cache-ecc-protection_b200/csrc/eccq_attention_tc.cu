@@ -15,16 +15,18 @@
 // per-head constants (QK^T) and into the running sum of weights (PV).
 //
 // One persistent CTA per SM, warp-specialised, all hand-offs through mbarriers:
-//   warp 0      producer: walks the block table, one cp.async.bulk (TMA) per K page, V page and scale row into a ring of
+//   warps 0, 3  producers (K / V): walk the block table, one cp.async.bulk (TMA) per page and scale row into a ring of
 //               128-token stages (complete_tx on the stage's "full" barrier)
 //   warp 1      MMA issuer (one thread): 4 + 4 tcgen05.mma per tile, tcgen05.commit to the barriers that hand S / O to the
 //               softmax warps and the stage back to the producer
-//   warp 2      query preparation for the next (sequence, kv-head, split) item: digits + constants, double buffered
-//   warp 3      TMEM allocation
+//   warp 2      TMEM allocation; query preparation for the next (sequence, kv-head, split) item: digits + constants,
+//               double buffered
 //   warps 4-7   softmax: thread = token (TMEM lane) for S, thread = dim for O; online softmax in base 2, fp32 state
 //   warps 8..   decode: LDS.128 raw codewords -> SWAR syndrome decode (eccq_common.cuh) -> STS.128 corrected nibbles IN PLACE
 //               at the 128-byte-swizzled position the UMMA descriptors expect
 // Partials (acc[D], m, l) per split go through the same workspace / attn_merge_kernel as the other attention kernels.
+#include <cuda.h>   // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
+
 #include "eccq_attention.h"
 
 namespace eccq {
@@ -32,7 +34,7 @@ namespace tc {
 
 constexpr int kTile = 128;                 // tokens per tile (= M of QK^T, K of PV)
 constexpr int kD = 128;                    // head_dim served by this kernel
-constexpr int kStages = 5;
+constexpr int kStages = 6;
 constexpr int kPartBytes = kTile * kD;     // one K or V tile: 16 KB
 constexpr int kStageBytes = 2 * kPartBytes + 2 * kTile * 4;   // K, V, k scales, v scales = 33 KB (multiple of 1024)
 constexpr int kQopBytes = 16 * 128;        // 16 digit rows x 128 dims
@@ -59,7 +61,9 @@ struct Misc {
 };
 constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc) + 1024;   // + alignment slack
 
-struct Args {
+struct alignas(64) Args {
+  // 2-D tensor maps for tile::gather4: K / V caches as rows of 2048 bytes (256 x u64), scales as rows of block_size floats
+  CUtensorMap tm_k, tm_v, tm_ks, tm_vs;
   CacheGeom g;
   const void* q;
   int q_dtype;
@@ -88,6 +92,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sptr(dst)), "l"(src), "r"(bytes), "r"(sptr(bar)) : "memory");
+}
+// four rows of a 2-D tensor (row indices r0..r3, column 0) -> 4 x row_bytes contiguous bytes at dst, ONE instruction
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* tm, int r0, int r1, int r2, int r3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(sptr(dst)), "l"(tm), "r"(sptr(bar)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -140,6 +149,23 @@ __device__ __forceinline__ bool get_item(const Args& a, int item, Item& it) {
   return it.ntiles > 0;
 }
 
+struct TileCursor {
+  int item, t;
+  Item it;
+  bool valid;
+};
+__device__ __forceinline__ void cursor_seek(const Args& a, int nitems, TileCursor& c) {   // c.item = candidate: skip empty items
+  while (c.item < nitems && !get_item(a, c.item, c.it)) c.item += gridDim.x;
+  c.valid = c.item < nitems;
+  c.t = 0;
+}
+__device__ __forceinline__ void cursor_next(const Args& a, int nitems, TileCursor& c) {
+  if (++c.t == c.it.ntiles) {
+    c.item += gridDim.x;
+    cursor_seek(a, nitems, c);
+  }
+}
+
 __device__ __forceinline__ float load_q(const void* q, int dtype, int64_t i) {
   if (dtype == ECCQ_F32) return reinterpret_cast<const float*>(q)[i];
   if (dtype == ECCQ_F16) return __half2float(reinterpret_cast<const __half*>(q)[i]);
@@ -158,7 +184,7 @@ __device__ __forceinline__ uint32_t decode_nibbles(uint32_t w, FlagCount& fc, bo
 }
 
 template <int CODEC, bool COUNT, int NDEC>
-__global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(const Args a, uint64_t* counters) {
+__global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(const __grid_constant__ Args a, uint64_t* counters) {
   extern __shared__ __align__(16) unsigned char eccq_tc_smem[];
   const uint32_t raw = sptr(eccq_tc_smem);
   unsigned char* const sm = eccq_tc_smem + ((1024u - (raw & 1023u)) & 1023u);
@@ -166,12 +192,13 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bs = a.g.bs;
   const int ppt = kTile / bs;                       // pages per tile
+  const int lgbs = 31 - __clz(bs);                  // block_size is a power of two (16 .. 128)
   const int nitems = a.nseq * a.g.H * a.npass * a.nsplit;
   const int G = a.Hq / a.g.H;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&mi.full[s], 1);
+      mbar_init(&mi.full[s], 2);   // one arrive.expect_tx per producer warp (K, V)
       mbar_init(&mi.kdec[s], NDEC);
       mbar_init(&mi.vdec[s], NDEC);
       mbar_init(&mi.empty[s], 1);
@@ -185,7 +212,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 3) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(sptr(&mi.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -194,36 +221,66 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
   tc_after();
   const uint32_t tmem = mi.tmem_base;   // columns [0,32): S buffers, [32,64): O buffers
 
-  if (warp == 0) {
-    // =============================================================== producer
-    const uint32_t page_tx = (uint32_t)(2 * bs * kD + 2 * bs * 4);
-    int n = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      Item it;
-      if (!get_item(a, item, it)) continue;
-      const int32_t* bt = a.block_table + (int64_t)it.seq * a.max_blocks;
-      for (int t = 0; t < it.ntiles; ++t, ++n) {
-        const int s = n % kStages;
-        if (lane == 0) mbar_wait(&mi.empty[s], ((n / kStages) & 1) ^ 1);
-        __syncwarp();
-        const int tok0 = (it.tile0 + t) * kTile + lane * bs;
-        const int lb = tok0 / bs;
-        int blk = -1;
-        if (lane < ppt && tok0 < it.c1 && lb < a.max_blocks) blk = bt[lb];
-        const uint32_t vm = __ballot_sync(0xFFFFFFFFu, blk >= 0);
-        unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
-        if (lane == 0) {
-          mi.page_mask[s] = vm;
-          mbar_arrive_tx(&mi.full[s], (uint32_t)__popc(vm) * page_tx);
-        }
-        if (blk >= 0) {
-          const int64_t page = page_index(a.g, blk, a.layer, it.kvh);
-          bulk_g2s(st + lane * bs * kD, a.g.k_cache + page * (int64_t)(bs * kD), (uint32_t)(bs * kD), &mi.full[s]);
-          bulk_g2s(st + kPartBytes + lane * bs * kD, a.g.v_cache + page * (int64_t)(bs * kD), (uint32_t)(bs * kD), &mi.full[s]);
-          bulk_g2s(st + 2 * kPartBytes + lane * bs * 4, a.g.k_scales + page * bs, (uint32_t)(bs * 4), &mi.full[s]);
-          bulk_g2s(st + 2 * kPartBytes + kTile * 4 + lane * bs * 4, a.vscales + page * bs, (uint32_t)(bs * 4), &mi.full[s]);
+  if (warp == 0 || warp == 3) {
+    // =============================================================== producers: warp 0 = K pages + K scales, warp 3 = V
+    // TMA tile::gather4: the four row coordinates of one instruction are four pages straight from the block table, so a
+    // 128-token tile is two instructions for the codewords and one or two for the scales (a plain cp.async.bulk per page
+    // costs ~100 cycles of issue latency each -- 32 per tile made the producer the bottleneck).  Pages that are unmapped or
+    // past the context are replaced by row 0 (loaded, then masked through page_mask), which keeps the byte count per stage
+    // constant.  The block-table entries of the NEXT tile are fetched before this tile's copies are issued.
+    const int part = warp == 0 ? 0 : 1;
+    const CUtensorMap* tm_c = part ? &a.tm_v : &a.tm_k;
+    const CUtensorMap* tm_s = part ? &a.tm_vs : &a.tm_ks;
+    const float* scales = part ? a.vscales : a.g.k_scales;
+    const int spp = bs >> 4;                        // 2048-byte rows per page
+    const int lgspp = lgbs - 4;
+    TileCursor c;
+    c.item = blockIdx.x;
+    cursor_seek(a, nitems, c);
+    auto fetch = [&](const TileCursor& tc_) -> int {
+      if (!tc_.valid) return -1;
+      const int tok0 = (tc_.it.tile0 + tc_.t) * kTile + lane * bs;
+      const int lb = tok0 >> lgbs;
+      return (lane < ppt && tok0 < tc_.it.c1 && lb < a.max_blocks) ? a.block_table[(int64_t)tc_.it.seq * a.max_blocks + lb] : -1;
+    };
+    int blk = fetch(c);
+    for (int n = 0; c.valid; ++n) {
+      const int kvh = c.it.kvh;
+      TileCursor nx = c;
+      cursor_next(a, nitems, nx);
+      const int blk_next = fetch(nx);
+      const uint32_t vm = __ballot_sync(0xFFFFFFFFu, blk >= 0);
+      const int page = blk >= 0 ? (blk * a.g.L + a.layer) * a.g.H + kvh : 0;       // lane j < ppt: page of the tile's j-th block
+      // lane j < 8: 2048-byte row j of the tile = sub-row (j % spp) of page (j / spp)
+      const int row = (__shfl_sync(0xFFFFFFFFu, page, (lane & 7) >> lgspp) << lgspp) + (lane & (spp - 1));
+      const int r0 = __shfl_sync(0xFFFFFFFFu, row, 0), r1 = __shfl_sync(0xFFFFFFFFu, row, 1), r2 = __shfl_sync(0xFFFFFFFFu, row, 2),
+                r3 = __shfl_sync(0xFFFFFFFFu, row, 3), r4 = __shfl_sync(0xFFFFFFFFu, row, 4), r5 = __shfl_sync(0xFFFFFFFFu, row, 5),
+                r6 = __shfl_sync(0xFFFFFFFFu, row, 6), r7 = __shfl_sync(0xFFFFFFFFu, row, 7);
+      const int p0 = __shfl_sync(0xFFFFFFFFu, page, 0), p1 = __shfl_sync(0xFFFFFFFFu, page, 1), p2 = __shfl_sync(0xFFFFFFFFu, page, 2),
+                p3 = __shfl_sync(0xFFFFFFFFu, page, 3), p4 = __shfl_sync(0xFFFFFFFFu, page, 4), p5 = __shfl_sync(0xFFFFFFFFu, page, 5),
+                p6 = __shfl_sync(0xFFFFFFFFu, page, 6), p7 = __shfl_sync(0xFFFFFFFFu, page, 7);
+      const int s = n % kStages;
+      unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
+      if (lane == 0) {
+        mbar_wait(&mi.empty[s], ((n / kStages) & 1) ^ 1);
+        if (part == 0) mi.page_mask[s] = vm;
+        mbar_arrive_tx(&mi.full[s], (uint32_t)(kPartBytes + kTile * 4));
+        tma_gather4(st + part * kPartBytes, tm_c, r0, r1, r2, r3, &mi.full[s]);
+        tma_gather4(st + part * kPartBytes + 8192, tm_c, r4, r5, r6, r7, &mi.full[s]);
+        unsigned char* sdst = st + 2 * kPartBytes + part * kTile * 4;
+        if (ppt == 8) {
+          tma_gather4(sdst, tm_s, p0, p1, p2, p3, &mi.full[s]);
+          tma_gather4(sdst + 256, tm_s, p4, p5, p6, p7, &mi.full[s]);
+        } else if (ppt == 4) {
+          tma_gather4(sdst, tm_s, p0, p1, p2, p3, &mi.full[s]);
+        } else {
+          bulk_g2s(sdst, scales + (int64_t)p0 * bs, (uint32_t)(bs * 4), &mi.full[s]);
+          if (ppt == 2) bulk_g2s(sdst + bs * 4, scales + (int64_t)p1 * bs, (uint32_t)(bs * 4), &mi.full[s]);
         }
       }
+      __syncwarp();
+      c = nx;
+      blk = blk_next;
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer (one thread)
@@ -390,7 +447,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
         const unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
         mbar_wait(&mi.full[s], (n / kStages) & 1);
         const int tok = (it.tile0 + t) * kTile + r;
-        const bool valid = tok < it.c1 && ((mi.page_mask[s] >> (r / bs)) & 1u);
+        const bool valid = tok < it.c1 && ((mi.page_mask[s] >> (r >> lgbs)) & 1u);
         const float ks = reinterpret_cast<const float*>(st + 2 * kPartBytes)[r];
         const float vs = valid ? reinterpret_cast<const float*>(st + 2 * kPartBytes + kTile * 4)[r] : 0.0f;
         mbar_wait(&mi.sready[b], (n >> 1) & 1);
@@ -519,7 +576,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
             const int row = (dw + i * NDEC) * 4 + (lane >> 3), c = lane & 7;
             const uint32_t base = sptr(st + part * kPartBytes + row * 128);
             wr[i] = base + (uint32_t)((c ^ (row & 7)) << 4);
-            cnt[i] = do_count && tokbase + row < it.c1 && ((pm >> (row / bs)) & 1u);
+            cnt[i] = do_count && tokbase + row < it.c1 && ((pm >> (row >> lgbs)) & 1u);
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x[i].x), "=r"(x[i].y), "=r"(x[i].z), "=r"(x[i].w) : "r"(base + (uint32_t)(c << 4)));
           }
           __syncwarp();
@@ -547,7 +604,43 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
   }
   tc_before();
   __syncthreads();
-  if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
+}
+
+// ---- host: tensor maps (encoded once per (buffer, geometry), cached) -----------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// rows x row_bytes bytes at `base`, box = one row; elem_bytes 8 (codeword rows, 256 elements) or 4 (scale rows)
+static bool tensor_map_rows(CUtensorMap& out, const void* base, uint64_t rows, uint32_t row_bytes, uint32_t elem_bytes) {
+  struct Entry { const void* base; uint64_t rows; uint32_t row_bytes; CUtensorMap tm; };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Entry& e : cache)
+    if (e.base == base && e.rows == rows && e.row_bytes == row_bytes) { out = e.tm; return true; }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t gdim[2] = {row_bytes / elem_bytes, rows};
+  const cuuint64_t gstr[1] = {row_bytes};
+  const cuuint32_t box[2] = {row_bytes / elem_bytes, 1};
+  const cuuint32_t estr[2] = {1, 1};
+  Entry e{base, rows, row_bytes, {}};
+  if (fn(&e.tm, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (cache.size() >= 64) cache.erase(cache.begin());
+  cache.push_back(e);
+  out = e.tm;
+  return true;
 }
 
 template <int CODEC, bool COUNT, int NDEC>
@@ -571,6 +664,12 @@ int try_attn_tc(const CacheGeom& g, AttnArgs& a, int q_dtype, uint64_t* counters
   if (!aligned16(g.k_cache) || !aligned16(g.v_cache) || !aligned16(g.k_scales) || !aligned16(g.v_scales)) return 0;
   const int G = a.Hq / g.H;
   tc::Args t;
+  const uint64_t pages = (uint64_t)g.nb * g.L * g.H;
+  if (pages * (uint64_t)(g.bs / 16) >= 0x7FFFFFFFull) return 0;
+  if (!tc::tensor_map_rows(t.tm_k, g.k_cache, pages * (g.bs / 16), 2048, 8) || !tc::tensor_map_rows(t.tm_v, g.v_cache, pages * (g.bs / 16), 2048, 8) ||
+      !tc::tensor_map_rows(t.tm_ks, g.k_scales, pages, (uint32_t)g.bs * 4, 4) ||
+      !tc::tensor_map_rows(t.tm_vs, a.v_use_k_scales ? g.k_scales : g.v_scales, pages, (uint32_t)g.bs * 4, 4))
+    return 0;
   t.g = g; t.q = a.q; t.q_dtype = q_dtype; t.block_table = a.block_table; t.context_lens = a.context_lens; t.ws = a.ws;
   t.vscales = a.v_use_k_scales ? g.k_scales : g.v_scales;
   t.max_blocks = a.max_blocks; t.nseq = a.nseq; t.Hq = a.Hq; t.layer = a.layer; t.sm_scale = a.sm_scale;
