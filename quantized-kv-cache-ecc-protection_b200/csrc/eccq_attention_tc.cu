@@ -39,9 +39,15 @@ constexpr int kPartBytes = kTile * kD;     // one K or V tile: 16 KB
 constexpr int kStageBytes = 2 * kPartBytes + 2 * kTile * 4;   // K, V, k scales, v scales = 33 KB (multiple of 1024)
 constexpr int kQopBytes = 16 * 128;        // 16 digit rows x 128 dims
 constexpr int kWBytes = kTile * 16;        // [token][16 weight bytes]
-constexpr int kFrontWarps = 8;             // producer, mma, query, tmem + 4 softmax
+constexpr int kFrontWarps = 12;            // roles 0-11: producer, S issuer, query/TMEM, PV issuer, 8 softmax
+constexpr int kSoftmaxWarps = 8;
+constexpr int kSoftmaxThreads = kSoftmaxWarps * 32;
+#ifndef ECCQ_TC_REVERSE_ROLES
+#define ECCQ_TC_REVERSE_ROLES 1            // roles are numbered from the LAST warp down: the issue arbiter favours high warp ids, and
+#endif                                     // the latency-critical roles (issuers, softmax, producers) should win over the decode warps
 constexpr int kHeadsPerPass = 4;           // q-heads per item: 4 heads x 4 digits = N 16
-constexpr uint32_t kSpinLimit = 1u << 26;
+constexpr uint32_t kSuspendNs = 1000000u;   // try_wait suspend-time hint: sleep until the barrier is touched
+constexpr uint32_t kSpinLimit = 1u << 24;   // x 4 probes, each sleeping up to the hint or until an arrival: seconds, then trap
 
 // ---- shared-memory map (offsets from a 1024-byte aligned base) -------------------------------------------------------
 constexpr int kOffStages = 0;
@@ -50,13 +56,14 @@ constexpr int kOffW = kOffQop + 2 * kQopBytes;
 constexpr int kOffMisc = kOffW + 2 * kWBytes;
 struct Misc {
   uint64_t full[kStages], kdec[kStages], vdec[kStages], empty[kStages];
-  uint64_t sready[2], wready[2], oready[2], qready[2], qfree[2];
+  uint64_t sready[2], sfree[2], wready[2], oready[2], qready[2], qfree[2];
   float qscale[2][kHeadsPerPass];        // 2^(e-27) * sm_scale * log2(e) per head (0 for unused heads)
   int32_t qc01[2][kHeadsPerPass];        // 8 * sum_d (d0*128 + d1)
   int32_t qc23[2][kHeadsPerPass];        // 8 * sum_d (d2*128 + d3)
-  float red[2][4][8];                    // per-tile exchange of the softmax warps: max score per head, max v scale
-  float fin[4][8];                       // end-of-item reduction: l and sum(w) per head per warp
+  float red[2][kSoftmaxWarps][4];        // rare-path exchange of the softmax warps: max score of the 2 heads, max v scale
+  float fin[kSoftmaxWarps][4];           // end-of-item reduction: l and sum(w) of the 2 heads per warp
   uint32_t page_mask[kStages];           // bit j: page j of the stage's tile was loaded
+  uint32_t pv_fresh[2];                  // 1: PV of this weight buffer starts a new accumulation in TMEM (written before wready)
   uint32_t tmem_base;
 };
 constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc) + 1024;   // + alignment slack
@@ -75,18 +82,40 @@ struct alignas(64) Args {
   float sm_scale;
 };
 
+// ---- optional pipeline trace (build with -DECCQ_TC_TRACE; tools/tc_trace.py): SM clock of every hand-off of CTA 0 ---------------
+#ifdef ECCQ_TC_TRACE
+__device__ long long g_tc_trace[512 * 16];
+#define TC_TRACE(n, ev)                                                                                   \
+  do {                                                                                                     \
+    if (blockIdx.x == 0 && (n) < 512) g_tc_trace[(n) * 16 + (ev)] = clock64();                            \
+  } while (0)
+#else
+#define TC_TRACE(n, ev) do { } while (0)
+#endif
+enum { EV_LOAD_ISSUE = 0, EV_DEC_START = 1, EV_DEC_K = 2, EV_DEC_V = 3, EV_S_ISSUE = 4, EV_SM_START = 5, EV_SM_W = 6, EV_PV_ISSUE = 7,
+       EV_O_READY = 8, EV_O_DONE = 9, EV_S_WAITK = 10, EV_LOAD_V = 11 };
+
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(b)), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(b)), "r"(bytes) : "memory"); }
-// every wait is bounded: a protocol bug traps instead of hanging the GPU
+// Every wait is bounded: a protocol bug traps instead of hanging the GPU.  try_wait carries a suspend-time hint: the warp
+// sleeps in hardware (NANOSLEEP on the barrier) and is woken by arrivals, so a waiting role costs a handful of issue slots
+// per wait.  Without the hint the probes spin through the issue slots the decode warps need (measured: 0.19 -> 0.27 ms); a
+// time-based bound around the hinted probe cost ~10 instructions per wake-up, half of the softmax warps' work.
+__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.b32 %0, 1, 0, p; }"
+               : "=r"(ok) : "r"(a), "r"(parity), "r"(kSuspendNs) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   const uint32_t a = sptr(b);
   for (uint32_t it = 0; it < kSpinLimit; ++it) {
-    uint32_t ok;
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    if (ok) return;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (mbar_try(a, parity)) return;
   }
   __trap();
 }
@@ -114,7 +143,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// barrier + OR-reduction of a predicate over the `nthreads` threads of named barrier `id`
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+  uint32_t out;
+  asm volatile("{ .reg .pred pi, po; setp.ne.u32 pi, %1, 0; bar.red.or.pred po, %2, %3, pi; selp.u32 %0, 1, 0, po; }"
+               : "=r"(out) : "r"((uint32_t)pred), "r"(id), "r"(nthreads) : "memory");
+  return out != 0;
+}
 __device__ __forceinline__ float warp_max_f32(float v) {
   float r;
   asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
@@ -189,7 +231,8 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
   const uint32_t raw = sptr(eccq_tc_smem);
   unsigned char* const sm = eccq_tc_smem + ((1024u - (raw & 1023u)) & 1023u);
   Misc& mi = *reinterpret_cast<Misc*>(sm + kOffMisc);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int warp = ECCQ_TC_REVERSE_ROLES ? (kFrontWarps + NDEC - 1) - (int)(threadIdx.x >> 5) : (int)(threadIdx.x >> 5);   // role index
   const int bs = a.g.bs;
   const int ppt = kTile / bs;                       // pages per tile
   const int lgbs = 31 - __clz(bs);                  // block_size is a power of two (16 .. 128)
@@ -198,17 +241,18 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&mi.full[s], 2);   // one arrive.expect_tx per producer warp (K, V)
+      mbar_init(&mi.full[s], 1);
       mbar_init(&mi.kdec[s], NDEC);
       mbar_init(&mi.vdec[s], NDEC);
       mbar_init(&mi.empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&mi.sready[b], 1);
-      mbar_init(&mi.wready[b], 128);
+      mbar_init(&mi.sfree[b], kSoftmaxThreads);
+      mbar_init(&mi.wready[b], kSoftmaxThreads);
       mbar_init(&mi.oready[b], 1);
       mbar_init(&mi.qready[b], 1);
-      mbar_init(&mi.qfree[b], 128);
+      mbar_init(&mi.qfree[b], kSoftmaxThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,21 +263,18 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
   tc_before();
   __syncthreads();
   tc_after();
-  const uint32_t tmem = mi.tmem_base;   // columns [0,32): S buffers, [32,64): O buffers
+  const uint32_t tmem = mi.tmem_base;   // columns [0,32): two S buffers, [32,48): the O accumulator
 
-  if (warp == 0 || warp == 3) {
-    // =============================================================== producers: warp 0 = K pages + K scales, warp 3 = V
+  if (warp == 0) {
+    // =============================================================== producer
     // TMA tile::gather4: the four row coordinates of one instruction are four pages straight from the block table, so a
-    // 128-token tile is two instructions for the codewords and one or two for the scales (a plain cp.async.bulk per page
-    // costs ~100 cycles of issue latency each -- 32 per tile made the producer the bottleneck).  Pages that are unmapped or
-    // past the context are replaced by row 0 (loaded, then masked through page_mask), which keeps the byte count per stage
-    // constant.  The block-table entries of the NEXT tile are fetched before this tile's copies are issued.
-    const int part = warp == 0 ? 0 : 1;
-    const CUtensorMap* tm_c = part ? &a.tm_v : &a.tm_k;
-    const CUtensorMap* tm_s = part ? &a.tm_vs : &a.tm_ks;
-    const float* scales = part ? a.vscales : a.g.k_scales;
+    // 128-token tile is 2 + 2 instructions for the K / V codewords and 1-2 + 1-2 for the scales (a plain cp.async.bulk per
+    // page costs ~100 cycles of issue latency each -- 32 per tile made the producer the bottleneck).  Pages that are unmapped
+    // or past the context are replaced by row 0 (loaded, then masked through page_mask), which keeps the byte count per
+    // stage constant.  The block-table entries of the NEXT tile are fetched before this tile's copies are issued.
     const int spp = bs >> 4;                        // 2048-byte rows per page
     const int lgspp = lgbs - 4;
+    const int lh0 = a.layer * a.g.H;
     TileCursor c;
     c.item = blockIdx.x;
     cursor_seek(a, nitems, c);
@@ -250,40 +291,54 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       cursor_next(a, nitems, nx);
       const int blk_next = fetch(nx);
       const uint32_t vm = __ballot_sync(0xFFFFFFFFu, blk >= 0);
-      const int page = blk >= 0 ? (blk * a.g.L + a.layer) * a.g.H + kvh : 0;       // lane j < ppt: page of the tile's j-th block
+      const int page = blk >= 0 ? blk * (a.g.L * a.g.H) + lh0 + kvh : 0;           // lane j < ppt: page of the tile's j-th block
       // lane j < 8: 2048-byte row j of the tile = sub-row (j % spp) of page (j / spp)
-      const int row = (__shfl_sync(0xFFFFFFFFu, page, (lane & 7) >> lgspp) << lgspp) + (lane & (spp - 1));
+      const int row = spp == 1 ? page : (__shfl_sync(0xFFFFFFFFu, page, (lane & 7) >> lgspp) << lgspp) + (lane & (spp - 1));
       const int r0 = __shfl_sync(0xFFFFFFFFu, row, 0), r1 = __shfl_sync(0xFFFFFFFFu, row, 1), r2 = __shfl_sync(0xFFFFFFFFu, row, 2),
                 r3 = __shfl_sync(0xFFFFFFFFu, row, 3), r4 = __shfl_sync(0xFFFFFFFFu, row, 4), r5 = __shfl_sync(0xFFFFFFFFu, row, 5),
                 r6 = __shfl_sync(0xFFFFFFFFu, row, 6), r7 = __shfl_sync(0xFFFFFFFFu, row, 7);
-      const int p0 = __shfl_sync(0xFFFFFFFFu, page, 0), p1 = __shfl_sync(0xFFFFFFFFu, page, 1), p2 = __shfl_sync(0xFFFFFFFFu, page, 2),
-                p3 = __shfl_sync(0xFFFFFFFFu, page, 3), p4 = __shfl_sync(0xFFFFFFFFu, page, 4), p5 = __shfl_sync(0xFFFFFFFFu, page, 5),
-                p6 = __shfl_sync(0xFFFFFFFFu, page, 6), p7 = __shfl_sync(0xFFFFFFFFu, page, 7);
+      int p0 = r0, p1 = r1, p2 = r2, p3 = r3;
+      if (spp != 1) { p0 = __shfl_sync(0xFFFFFFFFu, page, 0); p1 = __shfl_sync(0xFFFFFFFFu, page, 1); p2 = __shfl_sync(0xFFFFFFFFu, page, 2); p3 = __shfl_sync(0xFFFFFFFFu, page, 3); }
       const int s = n % kStages;
       unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
       if (lane == 0) {
         mbar_wait(&mi.empty[s], ((n / kStages) & 1) ^ 1);
-        if (part == 0) mi.page_mask[s] = vm;
-        mbar_arrive_tx(&mi.full[s], (uint32_t)(kPartBytes + kTile * 4));
-        tma_gather4(st + part * kPartBytes, tm_c, r0, r1, r2, r3, &mi.full[s]);
-        tma_gather4(st + part * kPartBytes + 8192, tm_c, r4, r5, r6, r7, &mi.full[s]);
-        unsigned char* sdst = st + 2 * kPartBytes + part * kTile * 4;
+        TC_TRACE(n, EV_LOAD_ISSUE);
+        mi.page_mask[s] = vm;
+        mbar_arrive_tx(&mi.full[s], (uint32_t)kStageBytes);
+        tma_gather4(st, &a.tm_k, r0, r1, r2, r3, &mi.full[s]);
+        tma_gather4(st + 8192, &a.tm_k, r4, r5, r6, r7, &mi.full[s]);
+        unsigned char* ksd = st + 2 * kPartBytes;
+        unsigned char* vsd = ksd + kTile * 4;
         if (ppt == 8) {
-          tma_gather4(sdst, tm_s, p0, p1, p2, p3, &mi.full[s]);
-          tma_gather4(sdst + 256, tm_s, p4, p5, p6, p7, &mi.full[s]);
+          tma_gather4(ksd, &a.tm_ks, r0, r1, r2, r3, &mi.full[s]);
+          tma_gather4(ksd + 256, &a.tm_ks, r4, r5, r6, r7, &mi.full[s]);
         } else if (ppt == 4) {
-          tma_gather4(sdst, tm_s, p0, p1, p2, p3, &mi.full[s]);
+          tma_gather4(ksd, &a.tm_ks, p0, p1, p2, p3, &mi.full[s]);
         } else {
-          bulk_g2s(sdst, scales + (int64_t)p0 * bs, (uint32_t)(bs * 4), &mi.full[s]);
-          if (ppt == 2) bulk_g2s(sdst + bs * 4, scales + (int64_t)p1 * bs, (uint32_t)(bs * 4), &mi.full[s]);
+          bulk_g2s(ksd, a.g.k_scales + (int64_t)p0 * bs, (uint32_t)(bs * 4), &mi.full[s]);
+          if (ppt == 2) bulk_g2s(ksd + bs * 4, a.g.k_scales + (int64_t)p1 * bs, (uint32_t)(bs * 4), &mi.full[s]);
+        }
+        tma_gather4(st + kPartBytes, &a.tm_v, r0, r1, r2, r3, &mi.full[s]);
+        tma_gather4(st + kPartBytes + 8192, &a.tm_v, r4, r5, r6, r7, &mi.full[s]);
+        if (ppt == 8) {
+          tma_gather4(vsd, &a.tm_vs, r0, r1, r2, r3, &mi.full[s]);
+          tma_gather4(vsd + 256, &a.tm_vs, r4, r5, r6, r7, &mi.full[s]);
+        } else if (ppt == 4) {
+          tma_gather4(vsd, &a.tm_vs, p0, p1, p2, p3, &mi.full[s]);
+        } else {
+          bulk_g2s(vsd, a.vscales + (int64_t)p0 * bs, (uint32_t)(bs * 4), &mi.full[s]);
+          if (ppt == 2) bulk_g2s(vsd + bs * 4, a.vscales + (int64_t)p1 * bs, (uint32_t)(bs * 4), &mi.full[s]);
         }
       }
       __syncwarp();
       c = nx;
       blk = blk_next;
     }
-  } else if (warp == 1) {
-    // =============================================================== MMA issuer (one thread)
+  } else if (warp == 1 || warp == 3) {
+    // =============================================================== MMA issuers (one thread each): role 1 = QK^T, role 3 = PV
+    // Two independent issue streams: S(n) goes out as soon as the K half of tile n is decoded and its TMEM buffer has been
+    // read; PV(n) as soon as the weights of tile n are written and the V half is decoded.  Neither waits for the other.
     if (lane == 0) {
       struct Cur { int item, t, n, j, ntiles; bool valid; };
       auto seek = [&](Cur& c) {   // c.item points at a candidate: skip empty items
@@ -296,37 +351,39 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
         ++c.n;
         if (++c.t == c.ntiles) { c.t = 0; ++c.j; c.item += gridDim.x; seek(c); }
       };
-      auto issue_s = [&](const Cur& c) {
-        const int s = c.n % kStages, b = c.n & 1, qb = c.j & 1;
-        if (c.t == 0) mbar_wait(&mi.qready[qb], (c.j >> 1) & 1);
-        mbar_wait(&mi.kdec[s], (c.n / kStages) & 1);
-        tc_after();
-        const uint32_t ka = sptr(sm + kOffStages + (size_t)s * kStageBytes), qa = sptr(sm + kOffQop + qb * kQopBytes);
+      Cur c{(int)blockIdx.x, 0, 0, 0, 0, false};
+      seek(c);
+      // descriptors differ from tile to tile only in the start-address field (bits 0-13, units of 16 bytes)
+      const uint64_t kdesc0 = smem_desc(sptr(sm + kOffStages), 16, 1024, 2), vdesc0 = smem_desc(sptr(sm + kOffStages + kPartBytes), 16, 1024, 2);
+      const uint64_t qdesc0 = smem_desc(sptr(sm + kOffQop), 16, 1024, 2), wdesc0 = smem_desc(sptr(sm + kOffW), 128, 256, 0);
+      if (warp == 1) {
+        for (; c.valid; advance(c)) {
+          const int s = c.n % kStages, b = c.n & 1, qb = c.j & 1;
+          if (c.t == 0) mbar_wait(&mi.qready[qb], (c.j >> 1) & 1);
+          mbar_wait(&mi.sfree[b], ((c.n >> 1) & 1) ^ 1);          // S(n-2) has been read out of this TMEM buffer
+          TC_TRACE(c.n, EV_S_WAITK);
+          mbar_wait(&mi.kdec[s], (c.n / kStages) & 1);
+          TC_TRACE(c.n, EV_S_ISSUE);
+          tc_after();
+          const uint64_t ka = kdesc0 + (uint64_t)(s * (kStageBytes >> 4)), qa = qdesc0 + (uint64_t)(qb * (kQopBytes >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_i8(tmem + b * 16, smem_desc(ka + k * 32, 16, 1024, 2), smem_desc(qa + k * 32, 16, 1024, 2), kIdescS, k > 0);
-        tc_commit(&mi.sready[b]);
-      };
-      auto issue_pv = [&](const Cur& c) {
-        const int s = c.n % kStages, b = c.n & 1;
-        mbar_wait(&mi.wready[b], (c.n >> 1) & 1);
-        mbar_wait(&mi.vdec[s], (c.n / kStages) & 1);
-        tc_after();
-        const uint32_t va = sptr(sm + kOffStages + (size_t)s * kStageBytes + kPartBytes), wa = sptr(sm + kOffW + b * kWBytes);
+          for (int k = 0; k < 4; ++k) tc_mma_i8(tmem + b * 16, ka + 2 * k, qa + 2 * k, kIdescS, k > 0);
+          tc_commit(&mi.sready[b]);
+        }
+      } else {
+        for (; c.valid; advance(c)) {
+          const int s = c.n % kStages, b = c.n & 1;
+          mbar_wait(&mi.wready[b], (c.n >> 1) & 1);               // W(n) and its fresh flag are in shared memory
+          mbar_wait(&mi.vdec[s], (c.n / kStages) & 1);
+          TC_TRACE(c.n, EV_PV_ISSUE);
+          tc_after();
+          const uint32_t keep = mi.pv_fresh[b] ? 0u : 1u;          // accumulate onto the previous tiles' product, or start over
+          const uint64_t va = vdesc0 + (uint64_t)(s * (kStageBytes >> 4)), wa = wdesc0 + (uint64_t)(b * (kWBytes >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_i8(tmem + 32 + b * 16, smem_desc(va + k * 4096, 16, 1024, 2), smem_desc(wa + k * 512, 128, 256, 0), kIdescO, k > 0);
-        tc_commit(&mi.oready[b]);
-        tc_commit(&mi.empty[s]);
-      };
-      Cur cs{(int)blockIdx.x, 0, 0, 0, 0, false}, cp;
-      seek(cs);
-      cp = cs;
-      if (cs.valid) { issue_s(cs); advance(cs); }
-      while (cp.valid) {
-        if (cs.valid) { issue_s(cs); advance(cs); }
-        issue_pv(cp);
-        advance(cp);
+          for (int k = 0; k < 4; ++k) tc_mma_i8(tmem + 32, va + 256 * k, wa + 32 * k, kIdescO, k > 0 ? 1u : keep);
+          tc_commit(&mi.oready[b]);
+          tc_commit(&mi.empty[s]);       // every MMA that reads this stage has completed (S(n) was consumed before W(n) existed)
+        }
       }
     }
   } else if (warp == 2) {
@@ -398,11 +455,16 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       if (lane == 0) mbar_arrive(&mi.qready[qb]);
       ++j;
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + kSoftmaxWarps) {
     // =============================================================== softmax / accumulate
-    const int w = warp - 4;
-    const int r = w * 32 + lane;                       // token row of S, dim row of O
+    // Eight warps: group g = 0/1 owns q-heads 2g, 2g+1 of the pass (S columns 8g..8g+7, the same columns of O, bytes 8g..8g+7
+    // of every weight row); thread = token row of S and dim row of O inside its TMEM lane quarter.
+    const int wi = warp - 4;                              // 0..7
+    const int g = wi >> 2;
+    const int w = (int)(threadIdx.x >> 5) & 3;            // TMEM lane quarter = physical warp id mod 4
+    const int r = w * 32 + lane;
     const uint32_t tlane = (uint32_t)(w * 32) << 16;
+    const bool tracer = wi == 0 && lane == 0;
     int n = 0, j = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       Item it;
@@ -410,37 +472,58 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       const int g0 = it.pass * kHeadsPerPass;
       const int ng = min(kHeadsPerPass, G - g0);
       if (!live) {   // empty split: neutral partial
-        for (int gi = 0; gi < ng; ++gi) {
-          float* wsrow = a.ws + (((int64_t)it.seq * a.Hq + it.kvh * G + g0 + gi) * a.nsplit + it.split) * (kD + 2);
-          wsrow[r] = 0.0f;
-          if (r == 0) { wsrow[kD] = -INFINITY; wsrow[kD + 1] = 0.0f; }
+        for (int hh = 0; hh < 2; ++hh) {
+          const int gi = 2 * g + hh;
+          if (gi < ng) {
+            float* wsrow = a.ws + (((int64_t)it.seq * a.Hq + it.kvh * G + g0 + gi) * a.nsplit + it.split) * (kD + 2);
+            wsrow[r] = 0.0f;
+            if (r == 0) { wsrow[kD] = -INFINITY; wsrow[kD + 1] = 0.0f; }
+          }
         }
         continue;
       }
       const int qb = j & 1;
       mbar_wait(&mi.qready[qb], (j >> 1) & 1);
-      float qs[4]; int32_t c01[4], c23[4];
+      float qs[2]; int32_t c01[2], c23[2];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) { qs[h] = mi.qscale[qb][h]; c01[h] = mi.qc01[qb][h]; c23[h] = mi.qc23[qb][h]; }
-      float m_run[4], l_thr[4], lw_thr[4], oacc[4];
+      for (int hh = 0; hh < 2; ++hh) { qs[hh] = mi.qscale[qb][2 * g + hh]; c01[hh] = mi.qc01[qb][2 * g + hh]; c23[hh] = mi.qc23[qb][2 * g + hh]; }
+      // Running state.  The PV products of consecutive tiles ACCUMULATE in TMEM (exact int32) for as long as neither the running
+      // maxima nor the weight scale move -- after the first tile of an item that is almost always -- so the steady state of a
+      // tile is: read S, one barrier-with-OR ("does anyone exceed the running maximum?"), exponentials, one 8-byte store.
+      // Lazy rescaling: the running maximum only moves when a score exceeds it by more than kSlack (base-2 units), so weights
+      // may reach 2^kSlack; the fixed-point format keeps 8 bits of headroom for that and 24 bits below one.  (With an exact
+      // running maximum every other tile of a 16-tile item set a new record for one of the four heads.)  A finite sentinel
+      // instead of -inf keeps the arithmetic free of special cases.
+      constexpr float kNegBig = -1.0e30f;
+      constexpr float kSlack = 8.0f;
+      float m_run[2], l_thr[2], lw_thr[2], oacc[2];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) { m_run[h] = -INFINITY; l_thr[h] = 0.0f; lw_thr[h] = 0.0f; oacc[h] = 0.0f; }
-      float sigma_prev = 0.0f;
-      auto drain_o = [&](int nn, const float (&scale)[4]) {   // O of tile nn (buffer nn & 1) -> oacc
-        const int b = nn & 1;
-        mbar_wait(&mi.oready[b], (nn >> 1) & 1);
+      for (int hh = 0; hh < 2; ++hh) { m_run[hh] = kNegBig; l_thr[hh] = 0.0f; lw_thr[hh] = 0.0f; oacc[hh] = 0.0f; }
+      uint32_t eb_run = 0;                 // biased exponent bound of the v scales seen so far
+      float wscale = 0.0f, sigma = 0.0f;   // 2^(24-E), 2^(E-24)
+      bool o_pending = false;              // TMEM holds products not yet folded into oacc
+      int o_waited = n - 1;                // last tile whose PV completion (oready phase) has been consumed
+      auto wait_o = [&](int nn) {          // every oready phase is consumed exactly once, in order
+        if (o_waited < nn) {
+          mbar_wait(&mi.oready[nn & 1], (nn >> 1) & 1);
+          if (tracer) TC_TRACE(nn, EV_O_READY);
+          o_waited = nn;
+        }
+      };
+      auto drain_o = [&]() {               // TMEM accumulator (relative to m_run / sigma) -> oacc
         tc_after();
-        uint32_t o[16];
-        tmem_ld16(tmem + 32 + b * 16 + tlane, o);
+        uint32_t o[8];
+        tmem_ld8(tmem + 32 + g * 8 + tlane, o);
         tc_before();
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          float v = __int2float_rn((int32_t)o[4 * h + 3]);
-          v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * h + 2]));
-          v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * h + 1]));
-          v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * h]));
-          oacc[h] = fmaf(v, scale[h], oacc[h]);
+        for (int hh = 0; hh < 2; ++hh) {
+          float v = __int2float_rn((int32_t)o[4 * hh + 3]);
+          v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * hh + 2]));
+          v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * hh + 1]));
+          v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * hh]));
+          oacc[hh] = fmaf(v, sigma, oacc[hh]);
         }
+        o_pending = false;
       };
       for (int t = 0; t < it.ntiles; ++t, ++n) {
         const int s = n % kStages, b = n & 1;
@@ -451,109 +534,122 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
         const float ks = reinterpret_cast<const float*>(st + 2 * kPartBytes)[r];
         const float vs = valid ? reinterpret_cast<const float*>(st + 2 * kPartBytes + kTile * 4)[r] : 0.0f;
         mbar_wait(&mi.sready[b], (n >> 1) & 1);
+        if (tracer) TC_TRACE(n, EV_SM_START);
         tc_after();
-        uint32_t sr[16];
-        tmem_ld16(tmem + b * 16 + tlane, sr);
+        uint32_t sr[8];
+        tmem_ld8(tmem + b * 16 + g * 8 + tlane, sr);
         tc_before();
-        float sc[4];
+        mbar_arrive(&mi.sfree[b]);
+        float sc[2];
+        bool need = (__float_as_uint(vs) >> 23) > eb_run;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int32_t hi = (int32_t)sr[4 * h] * 128 + (int32_t)sr[4 * h + 1] - c01[h];
-          const int32_t lo = (int32_t)sr[4 * h + 2] * 128 + (int32_t)sr[4 * h + 3] - c23[h];
+        for (int hh = 0; hh < 2; ++hh) {
+          const int32_t hi = (int32_t)sr[4 * hh] * 128 + (int32_t)sr[4 * hh + 1] - c01[hh];
+          const int32_t lo = (int32_t)sr[4 * hh + 2] * 128 + (int32_t)sr[4 * hh + 3] - c23[hh];
           const float f = fmaf(__int2float_rn(hi), 16384.0f, __int2float_rn(lo));
-          sc[h] = valid ? f * (ks * qs[h]) : -INFINITY;
+          sc[hh] = valid ? f * (ks * qs[hh]) : kNegBig;
+          need |= sc[hh] > m_run[hh] + kSlack;
         }
-        // ---- tile maxima: warp redux, then the four warps exchange through shared memory
-        {
-          float wm[4];
+        bool fresh = t == 0;
+        if (named_bar_or(1, kSoftmaxThreads, need)) {
+          // ---- rare: a maximum or the weight scale moves (for any head: PV starts over for all 16 columns at once).  Exchange
+          // the tile maxima, fold what TMEM holds into oacc under the old scales, rescale the running sums.
+          const float wm0 = warp_max_f32(sc[0]), wm1 = warp_max_f32(sc[1]), wv = warp_max_f32(vs);
+          if (lane == 0) *reinterpret_cast<float4*>(&mi.red[b][wi][0]) = make_float4(wm0, wm1, wv, 0.0f);
+          named_bar_sync(1, kSoftmaxThreads);
+          float tm0 = kNegBig, tm1 = kNegBig, vsmax = 0.0f;
 #pragma unroll
-          for (int h = 0; h < 4; ++h) wm[h] = warp_max_f32(sc[h]);
-          const float wv = warp_max_f32(vs);
-          if (lane == 0) {
-            *reinterpret_cast<float4*>(&mi.red[b][w][0]) = make_float4(wm[0], wm[1], wm[2], wm[3]);
-            mi.red[b][w][4] = wv;
+          for (int ww = 0; ww < 4; ++ww) {
+            const float4 x = *reinterpret_cast<const float4*>(&mi.red[b][g * 4 + ww][0]);
+            tm0 = fmaxf(tm0, x.x); tm1 = fmaxf(tm1, x.y); vsmax = fmaxf(vsmax, x.z);
           }
-        }
-        named_bar_sync(1, 128);
-        float alpha[4], vsmax = 0.0f;
+          if (o_pending) {
+            wait_o(n - 1);
+            drain_o();
+          }
+          const float tm[2] = {tm0, tm1};
 #pragma unroll
-        for (int ww = 0; ww < 4; ++ww) {
-          const float4 x = *reinterpret_cast<const float4*>(&mi.red[b][ww][0]);
-          if (ww == 0) { alpha[0] = x.x; alpha[1] = x.y; alpha[2] = x.z; alpha[3] = x.w; }
-          else { alpha[0] = fmaxf(alpha[0], x.x); alpha[1] = fmaxf(alpha[1], x.y); alpha[2] = fmaxf(alpha[2], x.z); alpha[3] = fmaxf(alpha[3], x.w); }
-          vsmax = fmaxf(vsmax, mi.red[b][ww][4]);
+          for (int hh = 0; hh < 2; ++hh) {
+            const float mn = fmaxf(m_run[hh], tm[hh]);
+            const float al = exp2f(m_run[hh] - mn);     // sentinel - finite underflows to 0, sentinel - sentinel = 0 gives 1
+            m_run[hh] = mn;
+            l_thr[hh] *= al;
+            lw_thr[hh] *= al;
+            oacc[hh] *= al;
+          }
+          // weights p * vs < 2^(kSlack + E) (E - 1 = exponent bound of the v scales) as 32-bit fixed point:
+          // wscale = 2^(24 - E), sigma = 1 / wscale
+          eb_run = max(eb_run, min(max(__float_as_uint(vsmax) >> 23, 24u), 254u));
+          wscale = __uint_as_float((277u - eb_run) << 23);
+          sigma = __uint_as_float((eb_run - 23u) << 23);
+          fresh = true;
         }
-        // weights as 32-bit fixed point relative to 2^E > vsmax: wscale = 2^(32-E), sigma = 2^(E-32)
-        const uint32_t eb = min(max(__float_as_uint(vsmax) >> 23, 32u), 254u);
-        const float wscale = __uint_as_float((285u - eb) << 23);
-        const float sigma = __uint_as_float((eb - 31u) << 23);
-        uint32_t wfix[4];
+        uint32_t wfix[2];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const float mn = fmaxf(m_run[h], alpha[h]);           // alpha[] holds the tile maximum here
-          const float al = (mn == -INFINITY) ? 1.0f : exp2f(m_run[h] - mn);
-          const float p = (sc[h] == -INFINITY) ? 0.0f : exp2f(sc[h] - mn);
+        for (int hh = 0; hh < 2; ++hh) {
+          const float p = valid ? exp2f(sc[hh] - m_run[hh]) : 0.0f;
           const float pw = p * vs;
-          m_run[h] = mn;
-          alpha[h] = al;
-          l_thr[h] = fmaf(l_thr[h], al, p);
-          lw_thr[h] = fmaf(lw_thr[h], al, pw);
-          oacc[h] *= al;
-          wfix[h] = __float2uint_rn(pw * wscale);
+          l_thr[hh] += p;
+          lw_thr[hh] += pw;
+          wfix[hh] = __float2uint_rn(pw * wscale);
         }
-        *reinterpret_cast<uint4*>(sm + kOffW + b * kWBytes + r * 16) = make_uint4(wfix[0], wfix[1], wfix[2], wfix[3]);
+        *reinterpret_cast<uint2*>(sm + kOffW + b * kWBytes + r * 16 + g * 8) = make_uint2(wfix[0], wfix[1]);
+        if (r == 0 && g == 0) mi.pv_fresh[b] = fresh ? 1u : 0u;
         fence_async_smem();
         mbar_arrive(&mi.wready[b]);
-        // ---- previous tile's O (relative to the previous running maximum): rescale by this tile's alpha
-        if (t > 0) {
-          const float sca[4] = {sigma_prev * alpha[0], sigma_prev * alpha[1], sigma_prev * alpha[2], sigma_prev * alpha[3]};
-          drain_o(n - 1, sca);
-        }
-        sigma_prev = sigma;
+        if (tracer) TC_TRACE(n, EV_SM_W);
+        o_pending = true;
+        if (t > 0) wait_o(n - 1);          // long complete by now; keeps the barrier phases in step
       }
-      {
-        const float sca[4] = {sigma_prev, sigma_prev, sigma_prev, sigma_prev};
-        drain_o(n - 1, sca);
-      }
-      // ---- end of item: sums over the 128 token threads, write the partial
+      wait_o(n - 1);
+      drain_o();
+      if (tracer) TC_TRACE(n - 1, EV_O_DONE);
+      // ---- end of item: sums over the 128 token threads of the group, write the partial
 #pragma unroll
-      for (int h = 0; h < 4; ++h)
+      for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          l_thr[h] += __shfl_xor_sync(0xFFFFFFFFu, l_thr[h], o);
-          lw_thr[h] += __shfl_xor_sync(0xFFFFFFFFu, lw_thr[h], o);
+          l_thr[hh] += __shfl_xor_sync(0xFFFFFFFFu, l_thr[hh], o);
+          lw_thr[hh] += __shfl_xor_sync(0xFFFFFFFFu, lw_thr[hh], o);
         }
-      if (lane == 0) {
-        *reinterpret_cast<float4*>(&mi.fin[w][0]) = make_float4(l_thr[0], l_thr[1], l_thr[2], l_thr[3]);
-        *reinterpret_cast<float4*>(&mi.fin[w][4]) = make_float4(lw_thr[0], lw_thr[1], lw_thr[2], lw_thr[3]);
-      }
-      named_bar_sync(1, 128);
-      float L[4] = {0, 0, 0, 0}, LW[4] = {0, 0, 0, 0};
+      if (lane == 0) *reinterpret_cast<float4*>(&mi.fin[wi][0]) = make_float4(l_thr[0], l_thr[1], lw_thr[0], lw_thr[1]);
+      named_bar_sync(1, kSoftmaxThreads);
+      float L[2] = {0, 0}, LW[2] = {0, 0};
 #pragma unroll
       for (int ww = 0; ww < 4; ++ww) {
-        const float4 x = *reinterpret_cast<const float4*>(&mi.fin[ww][0]);
-        const float4 y = *reinterpret_cast<const float4*>(&mi.fin[ww][4]);
-        L[0] += x.x; L[1] += x.y; L[2] += x.z; L[3] += x.w;
-        LW[0] += y.x; LW[1] += y.y; LW[2] += y.z; LW[3] += y.w;
+        const float4 x = *reinterpret_cast<const float4*>(&mi.fin[g * 4 + ww][0]);
+        L[0] += x.x; L[1] += x.y; LW[0] += x.z; LW[1] += x.w;
       }
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        if (h < ng) {
-          float* wsrow = a.ws + (((int64_t)it.seq * a.Hq + it.kvh * G + g0 + h) * a.nsplit + it.split) * (kD + 2);
-          wsrow[r] = fmaf(-8.0f, LW[h], oacc[h]);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int gi = 2 * g + hh;
+        if (gi < ng) {
+          float* wsrow = a.ws + (((int64_t)it.seq * a.Hq + it.kvh * G + g0 + gi) * a.nsplit + it.split) * (kD + 2);
+          wsrow[r] = fmaf(-8.0f, LW[hh], oacc[hh]);
           // the merge kernel works in natural-log units
-          if (r == 0) { wsrow[kD] = (m_run[h] == -INFINITY) ? -INFINITY : m_run[h] * 0.6931471805599453f; wsrow[kD + 1] = L[h]; }
+          if (r == 0) { wsrow[kD] = (m_run[hh] <= kNegBig) ? -INFINITY : m_run[hh] * 0.6931471805599453f; wsrow[kD + 1] = L[hh]; }
         }
       }
-      named_bar_sync(1, 128);          // mi.fin is reused by the next item
+      named_bar_sync(1, kSoftmaxThreads);          // mi.fin is reused by the next item
       mbar_arrive(&mi.qfree[qb]);
       ++j;
     }
   } else if (warp >= kFrontWarps) {
     // =============================================================== decode, in place
+    // Per tile and warp: the raw codewords of its K rows and V rows are loaded up front (LDS.128, one 512-byte run = 4 rows
+    // per warp instruction), decoded in registers and stored back to the SAME rows at the 128-byte-swizzled chunk position the
+    // UMMA descriptors expect; K is published first so QK^T overlaps the decoding of V.
     const int dw = warp - kFrontWarps;
-    constexpr int OPS = 32 / NDEC > 0 ? 32 / NDEC : 1;   // warp-wide 512-byte operations per part (K or V) per warp
-    static_assert(32 % NDEC == 0, "decode warps must divide the 32 row groups of a part");
+    constexpr int OPS = 32 / NDEC;   // warp-wide 512-byte operations per part (K or V) per warp
+    static_assert(NDEC > 0 && 32 % NDEC == 0, "decode warps must divide the 32 row groups of a part");
+    uint32_t rd_off[OPS], wr_off[OPS];
+#pragma unroll
+    for (int i = 0; i < OPS; ++i) {
+      const int row = (dw + i * NDEC) * 4 + (lane >> 3), c = lane & 7;
+      rd_off[i] = (uint32_t)(row * 128 + (c << 4));
+      wr_off[i] = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
+    }
+    const uint32_t stage0 = sptr(sm + kOffStages);
     FlagCount fc;
     int n = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -562,35 +658,38 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       const bool do_count = COUNT && it.pass == 0;
       for (int t = 0; t < it.ntiles; ++t, ++n) {
         const int s = n % kStages;
-        unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
+        const uint32_t st = stage0 + (uint32_t)(s * kStageBytes);
         mbar_wait(&mi.full[s], (n / kStages) & 1);
+        if (dw == 0 && lane == 0) TC_TRACE(n, EV_DEC_START);
         const uint32_t pm = COUNT ? mi.page_mask[s] : 0u;
         const int tokbase = (it.tile0 + t) * kTile;
+        uint4 x[2][OPS];
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int i = 0; i < OPS; ++i)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x[part][i].x), "=r"(x[part][i].y), "=r"(x[part][i].z), "=r"(x[part][i].w)
+                         : "r"(st + part * kPartBytes + rd_off[i]));
+        __syncwarp();
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
-          uint4 x[OPS];
-          uint32_t wr[OPS];
-          bool cnt[OPS];
 #pragma unroll
           for (int i = 0; i < OPS; ++i) {
-            const int row = (dw + i * NDEC) * 4 + (lane >> 3), c = lane & 7;
-            const uint32_t base = sptr(st + part * kPartBytes + row * 128);
-            wr[i] = base + (uint32_t)((c ^ (row & 7)) << 4);
-            cnt[i] = do_count && tokbase + row < it.c1 && ((pm >> (row >> lgbs)) & 1u);
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x[i].x), "=r"(x[i].y), "=r"(x[i].z), "=r"(x[i].w) : "r"(base + (uint32_t)(c << 4)));
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < OPS; ++i) {
-            const uint32_t y0 = decode_nibbles<CODEC, COUNT>(x[i].x, fc, cnt[i]);
-            const uint32_t y1 = decode_nibbles<CODEC, COUNT>(x[i].y, fc, cnt[i]);
-            const uint32_t y2 = decode_nibbles<CODEC, COUNT>(x[i].z, fc, cnt[i]);
-            const uint32_t y3 = decode_nibbles<CODEC, COUNT>(x[i].w, fc, cnt[i]);
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(wr[i]), "r"(y0), "r"(y1), "r"(y2), "r"(y3) : "memory");
+            bool cnt = false;
+            if (COUNT) {
+              const int row = (dw + i * NDEC) * 4 + (lane >> 3);
+              cnt = do_count && tokbase + row < it.c1 && ((pm >> (row >> lgbs)) & 1u);
+            }
+            const uint32_t y0 = decode_nibbles<CODEC, COUNT>(x[part][i].x, fc, cnt);
+            const uint32_t y1 = decode_nibbles<CODEC, COUNT>(x[part][i].y, fc, cnt);
+            const uint32_t y2 = decode_nibbles<CODEC, COUNT>(x[part][i].z, fc, cnt);
+            const uint32_t y3 = decode_nibbles<CODEC, COUNT>(x[part][i].w, fc, cnt);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(st + part * kPartBytes + wr_off[i]), "r"(y0), "r"(y1), "r"(y2), "r"(y3) : "memory");
           }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(part == 0 ? &mi.kdec[s] : &mi.vdec[s]);
+          if (dw == 0 && lane == 0) TC_TRACE(n, part == 0 ? EV_DEC_K : EV_DEC_V);
         }
       }
     }
@@ -654,6 +753,12 @@ static int launch(const Args& a, uint64_t* counters, cudaStream_t st) {
 }
 
 }  // namespace tc
+
+#ifdef ECCQ_TC_TRACE
+extern "C" int eccq_tc_trace_read(long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, tc::g_tc_trace, sizeof(long long) * 512 * 16) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 // returns 1 when the tcgen05 kernel took the launch (partials written; the caller runs the merge), 0 when the geometry is
 // outside it, < 0 on error.  May lower a.nsplit / raise a.chunk (fewer, longer splits; the workspace was sized for more).
