@@ -241,7 +241,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&mi.full[s], 1);
+      mbar_init(&mi.full[s], 2);   // one arrive.expect_tx per producer warp (K, V)
       mbar_init(&mi.kdec[s], NDEC);
       mbar_init(&mi.vdec[s], NDEC);
       mbar_init(&mi.empty[s], 1);
@@ -265,13 +265,19 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
   tc_after();
   const uint32_t tmem = mi.tmem_base;   // columns [0,32): two S buffers, [32,48): the O accumulator
 
-  if (warp == 0) {
-    // =============================================================== producer
+  if (warp == 0 || warp == 2) {
+    // =============================================================== producers: role 0 = K codewords + K scales (and the
+    // query digits of every new item), role 2 = V codewords + V scales
     // TMA tile::gather4: the four row coordinates of one instruction are four pages straight from the block table, so a
-    // 128-token tile is 2 + 2 instructions for the K / V codewords and 1-2 + 1-2 for the scales (a plain cp.async.bulk per
-    // page costs ~100 cycles of issue latency each -- 32 per tile made the producer the bottleneck).  Pages that are unmapped
-    // or past the context are replaced by row 0 (loaded, then masked through page_mask), which keeps the byte count per
-    // stage constant.  The block-table entries of the NEXT tile are fetched before this tile's copies are issued.
+    // 128-token tile is 2 instructions for the codewords and 1-2 for the scales per producer (a plain cp.async.bulk per page
+    // costs ~100 cycles of issue latency each -- 32 per tile made the producer the bottleneck; so did ONE warp issuing all 8
+    // gathers of a tile: ~2400 cycles per tile).  Pages that are unmapped or past the context are replaced by row 0 (loaded,
+    // then masked through page_mask), which keeps the byte count per stage constant.  The block-table entries of the NEXT
+    // tile are fetched before this tile's copies are issued.
+    const int part = warp == 0 ? 0 : 1;
+    const CUtensorMap* tm_c = part ? &a.tm_v : &a.tm_k;
+    const CUtensorMap* tm_s = part ? &a.tm_vs : &a.tm_ks;
+    const float* scales = part ? a.vscales : a.g.k_scales;
     const int spp = bs >> 4;                        // 2048-byte rows per page
     const int lgspp = lgbs - 4;
     const int lh0 = a.layer * a.g.H;
@@ -285,8 +291,11 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       return (lane < ppt && tok0 < tc_.it.c1 && lb < a.max_blocks) ? a.block_table[(int64_t)tc_.it.seq * a.max_blocks + lb] : -1;
     };
     int blk = fetch(c);
+    int j = 0;                                      // non-empty items started (query buffer = j & 1)
     for (int n = 0; c.valid; ++n) {
       const int kvh = c.it.kvh;
+      const bool new_item = c.t == 0;
+      const Item it = c.it;
       TileCursor nx = c;
       cursor_next(a, nitems, nx);
       const int blk_next = fetch(nx);
@@ -303,35 +312,88 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
       if (lane == 0) {
         mbar_wait(&mi.empty[s], ((n / kStages) & 1) ^ 1);
-        TC_TRACE(n, EV_LOAD_ISSUE);
-        mi.page_mask[s] = vm;
-        mbar_arrive_tx(&mi.full[s], (uint32_t)kStageBytes);
-        tma_gather4(st, &a.tm_k, r0, r1, r2, r3, &mi.full[s]);
-        tma_gather4(st + 8192, &a.tm_k, r4, r5, r6, r7, &mi.full[s]);
-        unsigned char* ksd = st + 2 * kPartBytes;
-        unsigned char* vsd = ksd + kTile * 4;
+        TC_TRACE(n, part ? EV_LOAD_V : EV_LOAD_ISSUE);
+        if (part == 0) mi.page_mask[s] = vm;
+        mbar_arrive_tx(&mi.full[s], (uint32_t)(kPartBytes + kTile * 4));
+        tma_gather4(st + part * kPartBytes, tm_c, r0, r1, r2, r3, &mi.full[s]);
+        tma_gather4(st + part * kPartBytes + 8192, tm_c, r4, r5, r6, r7, &mi.full[s]);
+        unsigned char* sdst = st + 2 * kPartBytes + part * kTile * 4;
         if (ppt == 8) {
-          tma_gather4(ksd, &a.tm_ks, r0, r1, r2, r3, &mi.full[s]);
-          tma_gather4(ksd + 256, &a.tm_ks, r4, r5, r6, r7, &mi.full[s]);
+          tma_gather4(sdst, tm_s, r0, r1, r2, r3, &mi.full[s]);
+          tma_gather4(sdst + 256, tm_s, r4, r5, r6, r7, &mi.full[s]);
         } else if (ppt == 4) {
-          tma_gather4(ksd, &a.tm_ks, p0, p1, p2, p3, &mi.full[s]);
+          tma_gather4(sdst, tm_s, p0, p1, p2, p3, &mi.full[s]);
         } else {
-          bulk_g2s(ksd, a.g.k_scales + (int64_t)p0 * bs, (uint32_t)(bs * 4), &mi.full[s]);
-          if (ppt == 2) bulk_g2s(ksd + bs * 4, a.g.k_scales + (int64_t)p1 * bs, (uint32_t)(bs * 4), &mi.full[s]);
-        }
-        tma_gather4(st + kPartBytes, &a.tm_v, r0, r1, r2, r3, &mi.full[s]);
-        tma_gather4(st + kPartBytes + 8192, &a.tm_v, r4, r5, r6, r7, &mi.full[s]);
-        if (ppt == 8) {
-          tma_gather4(vsd, &a.tm_vs, r0, r1, r2, r3, &mi.full[s]);
-          tma_gather4(vsd + 256, &a.tm_vs, r4, r5, r6, r7, &mi.full[s]);
-        } else if (ppt == 4) {
-          tma_gather4(vsd, &a.tm_vs, p0, p1, p2, p3, &mi.full[s]);
-        } else {
-          bulk_g2s(vsd, a.vscales + (int64_t)p0 * bs, (uint32_t)(bs * 4), &mi.full[s]);
-          if (ppt == 2) bulk_g2s(vsd + bs * 4, a.vscales + (int64_t)p1 * bs, (uint32_t)(bs * 4), &mi.full[s]);
+          bulk_g2s(sdst, scales + (int64_t)p0 * bs, (uint32_t)(bs * 4), &mi.full[s]);
+          if (ppt == 2) bulk_g2s(sdst + bs * 4, scales + (int64_t)p1 * bs, (uint32_t)(bs * 4), &mi.full[s]);
         }
       }
       __syncwarp();
+      if (part == 0 && new_item) {
+        // ---- query digits of the item whose first tile was just requested (the loads run ~4 tiles ahead of the MMAs)
+        const int qb = j & 1;
+        mbar_wait(&mi.qfree[qb], ((j >> 1) & 1) ^ 1);
+        const int hh = lane >> 3, c = lane & 7;               // head of the pass, 16-dim chunk
+        const int g0 = it.pass * kHeadsPerPass;
+        const bool used = g0 + hh < G;
+        float v[16];
+        float amax = 0.0f;
+        const int64_t qbase = ((int64_t)it.seq * a.Hq + (int64_t)it.kvh * G + g0 + hh) * kD + c * 16;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          v[e] = used ? load_q(a.q, a.q_dtype, qbase + e) : 0.0f;
+          amax = fmaxf(amax, fabsf(v[e]));
+        }
+        amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 2));
+        amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 4));
+        // amax = m * 2^ex with m in [0.5, 1): |q| * 2^(27-ex) < 2^27
+        int ex = 0;
+        if (amax > 0.0f && amax < INFINITY) (void)frexpf(amax, &ex);
+        const float up = ldexpf(1.0f, 27 - ex);
+        uint32_t dig[4][4];   // [digit][word of 4 dims]
+        int32_t s01 = 0, s23 = 0;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+          uint32_t pk[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            int32_t x = __float2int_rn(v[w4 * 4 + e] * up);
+            const int32_t d3 = ((x + 64) & 127) - 64; x = (x - d3) >> 7;
+            const int32_t d2 = ((x + 64) & 127) - 64; x = (x - d2) >> 7;
+            const int32_t d1 = ((x + 64) & 127) - 64; x = (x - d1) >> 7;
+            const int32_t d0 = x;
+            s01 += d0 * 128 + d1;
+            s23 += d2 * 128 + d3;
+            pk[0] |= (uint32_t)(d0 & 0xFF) << (8 * e);
+            pk[1] |= (uint32_t)(d1 & 0xFF) << (8 * e);
+            pk[2] |= (uint32_t)(d2 & 0xFF) << (8 * e);
+            pk[3] |= (uint32_t)(d3 & 0xFF) << (8 * e);
+          }
+#pragma unroll
+          for (int l = 0; l < 4; ++l) dig[l][w4] = pk[l];
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          s01 += __shfl_xor_sync(0xFFFFFFFFu, s01, o);
+          s23 += __shfl_xor_sync(0xFFFFFFFFu, s23, o);
+        }
+        unsigned char* qop = sm + kOffQop + qb * kQopBytes;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int row = hh * 4 + l;
+          *reinterpret_cast<uint4*>(qop + row * 128 + ((c ^ (row & 7)) << 4)) = make_uint4(dig[l][0], dig[l][1], dig[l][2], dig[l][3]);
+        }
+        if (c == 0) {
+          mi.qscale[qb][hh] = used ? ldexpf(a.sm_scale * 1.4426950408889634f, ex - 27) : 0.0f;
+          mi.qc01[qb][hh] = 8 * s01;
+          mi.qc23[qb][hh] = 8 * s23;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mi.qready[qb]);
+        ++j;
+      }
       c = nx;
       blk = blk_next;
     }
@@ -385,75 +447,6 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
           tc_commit(&mi.empty[s]);       // every MMA that reads this stage has completed (S(n) was consumed before W(n) existed)
         }
       }
-    }
-  } else if (warp == 2) {
-    // =============================================================== query digits for the next item
-    int j = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      Item it;
-      if (!get_item(a, item, it)) continue;
-      const int qb = j & 1;
-      mbar_wait(&mi.qfree[qb], ((j >> 1) & 1) ^ 1);
-      const int hh = lane >> 3, c = lane & 7;               // head of the pass, 16-dim chunk
-      const int g0 = it.pass * kHeadsPerPass;
-      const bool used = g0 + hh < G;
-      float v[16];
-      float amax = 0.0f;
-      const int64_t qbase = ((int64_t)it.seq * a.Hq + (int64_t)it.kvh * G + g0 + hh) * kD + c * 16;
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        v[e] = used ? load_q(a.q, a.q_dtype, qbase + e) : 0.0f;
-        amax = fmaxf(amax, fabsf(v[e]));
-      }
-      amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 1));
-      amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 2));
-      amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 4));
-      // amax = m * 2^ex with m in [0.5, 1): |q| * 2^(27-ex) < 2^27
-      int ex = 0;
-      if (amax > 0.0f && amax < INFINITY) (void)frexpf(amax, &ex);
-      const float up = ldexpf(1.0f, 27 - ex);
-      uint32_t dig[4][4];   // [digit][word of 4 dims]
-      int32_t s01 = 0, s23 = 0;
-#pragma unroll
-      for (int w4 = 0; w4 < 4; ++w4) {
-        uint32_t pk[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          int32_t x = __float2int_rn(v[w4 * 4 + e] * up);
-          const int32_t d3 = ((x + 64) & 127) - 64; x = (x - d3) >> 7;
-          const int32_t d2 = ((x + 64) & 127) - 64; x = (x - d2) >> 7;
-          const int32_t d1 = ((x + 64) & 127) - 64; x = (x - d1) >> 7;
-          const int32_t d0 = x;
-          s01 += d0 * 128 + d1;
-          s23 += d2 * 128 + d3;
-          pk[0] |= (uint32_t)(d0 & 0xFF) << (8 * e);
-          pk[1] |= (uint32_t)(d1 & 0xFF) << (8 * e);
-          pk[2] |= (uint32_t)(d2 & 0xFF) << (8 * e);
-          pk[3] |= (uint32_t)(d3 & 0xFF) << (8 * e);
-        }
-#pragma unroll
-        for (int l = 0; l < 4; ++l) dig[l][w4] = pk[l];
-      }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
-        s01 += __shfl_xor_sync(0xFFFFFFFFu, s01, o);
-        s23 += __shfl_xor_sync(0xFFFFFFFFu, s23, o);
-      }
-      unsigned char* qop = sm + kOffQop + qb * kQopBytes;
-#pragma unroll
-      for (int l = 0; l < 4; ++l) {
-        const int row = hh * 4 + l;
-        *reinterpret_cast<uint4*>(qop + row * 128 + ((c ^ (row & 7)) << 4)) = make_uint4(dig[l][0], dig[l][1], dig[l][2], dig[l][3]);
-      }
-      if (c == 0) {
-        mi.qscale[qb][hh] = used ? ldexpf(a.sm_scale * 1.4426950408889634f, ex - 27) : 0.0f;
-        mi.qc01[qb][hh] = 8 * s01;
-        mi.qc23[qb][hh] = 8 * s23;
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&mi.qready[qb]);
-      ++j;
     }
   } else if (warp >= 4 && warp < 4 + kSoftmaxWarps) {
     // =============================================================== softmax / accumulate
