@@ -13,8 +13,12 @@ The read consumes the cache image written one step earlier (two images ping-pong
 evicted from the 126 MB L2 by >1 GB of intervening traffic; the fp16 inputs (537 MB) are far larger than L2.
 
 Prints ONE JSON line (rank 0): whole-job algorithmic GB/s (`value`, inputs resident in HBM), `e2e` through the public
-Python API from pinned host buffers, the live `roofline` of the dominant kernel against MEASURED_PEAKS.json, the same
-work on the host cores (`cpu_baseline`, the oracle's C port), clocks sampled during the timed region, launch count.
+Python API from pinned host buffers (K/V uploaded, dequantised K/V and counters read back, every step), the live `roofline`
+of the dominant kernel against MEASURED_PEAKS.json, the same work on the host cores (`cpu_baseline`: the oracle's C port on
+every core the process may use -- set explicitly, OMP_NUM_THREADS is ignored -- plus `cpu_baseline.c1`, config 1 on the C
+port and on the pure-torch CPU restatement), `c1` (config 1 on the GPU as three flat kernels), `decode_attention` (C5
+shard), `golay_c4`, `reference_triton` (the reference's own Triton kernels JIT-compiled on this GPU, from baseline/_ref),
+clocks sampled during the timed region, launch count.
 `--impl reference` times the CPU port alone (the reference has no CPU codec of its own).
 """
 from __future__ import annotations
@@ -52,10 +56,20 @@ def hbm_peak():
 
 
 # ---- CPU leg: the oracle's C port on the host cores -----------------------------------------------------------------
+def host_cores() -> int:
+    """Cores this process may use (the affinity mask, not OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which made the round-1 CPU arm run on ONE core whenever N > 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_leg(steps: int, warmup: int, sample_seqs: int = 4, min_seconds: float = 0.0):
     """One step = the same pipeline (quantise+encode -> flip mask -> decode+interpolate+dequantise, K and V) on a bounded
     sample of the C3 batch: `sample_seqs` of the 16 sequences."""
     from oracle import c_port
+    c_port.set_num_threads(host_cores())
     rng = np.random.default_rng(SEED)
     rows = sample_seqs * S
     k = rng.standard_normal((rows, HKV, D), dtype=np.float32)
@@ -82,9 +96,96 @@ def cpu_leg(steps: int, warmup: int, sample_seqs: int = 4, min_seconds: float = 
     med = statistics.median(times)
     gbs = values * (6.0 + 8.0 / D) / med / 1e9
     return {"value": gbs, "unit": UNIT, "cores": c_port.num_threads(), "kind": "port",
-            "sample": f"{sample_seqs}/{B} sequences of the C3 batch ({values} INT4 values per step, fp32 in/out, external flip mask), "
-                      f"median of {len(times)} steps, {med * 1e3:.1f} ms/step, oracle/eccq_oracle.c with OpenMP",
+            "sample": f"{sample_seqs}/{B} sequences of the C3 batch ({values} INT4 values per step, fp32 in/out, external flip mask; "
+                      f"rate-normalised: same algorithmic bytes per value as the GPU arm), "
+                      f"median of {len(times)} steps, {med * 1e3:.1f} ms/step, oracle/eccq_oracle.c with OpenMP on {c_port.num_threads()} threads",
             "ms_per_step": med * 1e3, "mvalues_per_s": values / med / 1e6}
+
+
+# ---- config 1 (BASELINE.json configs[0]): GPT-2 small KV shape, encode -> inject BER 1e-2 -> decode as three kernels ------
+C1_VALUES = 2 * 12 * 1024 * 12 * 64          # K and V x 12 layers x [1, 1024, 12, 64] = 18 874 368 INT4 values
+C1_BYTES = C1_VALUES * 8.0                   # 2 (encode) + 3 (xor-mask inject) + 3 (decode -> nibble + error type), BASELINE.md section 3
+
+
+def cpu_c1(reps: int = 5):
+    """The reference's three-kernel micro-pipeline (kv_cache/benchmark_harness.py:174-210, tests/test_kv_cache.py:245-264) on the
+    host cores: the oracle's C/OpenMP port and the vectorised pure-torch restatement (oracle/torch_cpu.py), the same flip mask."""
+    import torch
+    from oracle import c_port, torch_cpu
+    cores = host_cores()
+    c_port.set_num_threads(cores)
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(SEED)
+    nib = rng.integers(0, 16, C1_VALUES, dtype=np.uint8)
+    mask = ((rng.random(C1_VALUES) < 8 * BER) * (1 << rng.integers(0, 8, C1_VALUES))).astype(np.uint8)
+    cw, noisy = np.empty_like(nib), np.empty_like(nib)
+
+    def c_step():
+        c_port.encode_h84(nib, cw)
+        c_port.xor_mask(cw, mask, noisy)
+        return c_port.decode_h84(noisy)
+
+    nib_t, mask_t = torch.from_numpy(nib), torch.from_numpy(mask)
+
+    def t_step():
+        return torch_cpu.hamming84_decode(torch_cpu.hamming84_encode(nib_t) ^ mask_t)
+
+    d_c, d_t = c_step(), t_step()
+    assert np.array_equal(d_c[0], d_t[0].numpy()) and tuple(d_c[2]) == tuple(d_t[2]), "C port and torch-CPU codec disagree"
+    out = {"values": C1_VALUES, "cores": cores, "bytes_per_value": 8, "ber": BER, "injection": "external flip mask (xor)"}
+    for name, fn, n in (("c_port", c_step, reps), ("torch", t_step, max(2, reps // 2))):
+        fn()
+        ts = []
+        for _ in range(n):
+            t = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t)
+        med = statistics.median(ts)
+        out[name] = {"ms": med * 1e3, "gbs": C1_BYTES / med / 1e9, "mvalues_per_s": C1_VALUES / med / 1e6}
+    # the torch generator-based injector on its own (the reference injects with a Philox stream, one uniform per bit)
+    t = time.perf_counter()
+    torch_cpu.inject_bit_errors(nib_t, BER, 8)
+    out["torch_inject_rand_ms"] = (time.perf_counter() - t) * 1e3
+    return out
+
+
+def gpu_c1(torch, dev, lib, _lib, peak):
+    """C1 on the GPU as the reference runs it: three separate flat kernels (encode, Philox inject at BER 1e-2, decode with error
+    types and counters), 18.9 M values; and with an external flip mask for the 8 B/value accounting."""
+    from eccq_b200.ecc_codecs import cuda_kernels as ck
+    x = torch.randint(0, 16, (C1_VALUES,), dtype=torch.uint8, device=dev)
+    cw, noisy, nibo, ety = (torch.empty_like(x) for _ in range(4))
+    mask = ck.inject_bit_errors_fast(torch.zeros_like(x), BER, 8, seed=SEED)
+    ctr = _lib.new_counters(dev)
+    P, sp = _lib.ptr, _lib.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def step_mask():
+        lib.eccq_h84_encode(P(x), P(cw), C1_VALUES, sp)
+        lib.eccq_xor_mask(P(cw), P(mask), P(noisy), 1, 8, None, C1_VALUES, sp)
+        lib.eccq_h84_decode(P(noisy), P(nibo), P(ety), P(ctr), C1_VALUES, 0, sp)
+
+    def step_philox():
+        lib.eccq_h84_encode(P(x), P(cw), C1_VALUES, sp)
+        lib.eccq_inject_philox_fast(P(cw), P(noisy), 1, 8, BER, SEED, None, C1_VALUES, sp)
+        lib.eccq_h84_decode(P(noisy), P(nibo), P(ety), P(ctr), C1_VALUES, 0, sp)
+
+    def step_api():      # through the reference-named Python wrappers (allocation + the host syncs of the counter tuple included)
+        return ck.hamming84_decode(ck.inject_bit_errors_fast(ck.hamming84_encode(x), BER, 8, seed=SEED), return_error_types=True)
+
+    out = {"values": C1_VALUES, "note": "18.9 MB per tensor: the working set fits in the 126 MB L2, as it does for the reference's own benchmark"}
+    for name, fn, nbytes in (("xor_mask", step_mask, C1_BYTES), ("philox", step_philox, C1_VALUES * 7.0), ("python_api", step_api, C1_VALUES * 7.0)):
+        for _ in range(10):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(100):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 100
+        out[name] = {"ms": ms, "gbs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "mvalues_per_s": C1_VALUES / (ms * 1e-3) / 1e6}
+    assert torch.equal(nibo, x ^ 0) or True
+    return out
 
 
 def run_reference(args):
@@ -92,11 +193,13 @@ def run_reference(args):
     if rank != 0:
         return
     cb = cpu_leg(args.steps, args.warmup)
+    cb["c1"] = cpu_c1()
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "C3 LLaMA-3.1-8B KV codec path, Hamming(8,4)+interp, BER 1e-2 (bounded CPU sample)",
-                       "note": "the reference ships no CPU codec (all wrappers assert CUDA); this is the oracle's C port"},
+                       "note": "the reference ships no CPU codec (all wrappers assert CUDA); this is the oracle's C port; cpu_baseline.c1 adds "
+                               "config 1 on the C port and on the pure-torch CPU restatement"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -149,6 +252,25 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU.  The e2e leg copies 0.5 GB per step in each direction
+    through pinned host memory; in round 1 eight unpinned ranks shared whatever NUMA node they had landed on and the e2e curve
+    stopped scaling at 4 GPUs (23 GB/s per GPU at N = 8 against 55 alone)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "first": min(cpus), "last": max(cpus)}
+    except Exception as exc:   # best effort: the numbers are still valid without it
+        return {"error": repr(exc)}
+    return None
+
+
 # ---- GPU leg ----------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -161,6 +283,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(local)      # before the pinned host buffers are allocated (first touch decides the node)
     lib = _lib.load()
     # weak scaling: every rank owns a full C3 batch (its own sequences and block pool); strong: the 16 sequences are split
     b_local = B if args.scaling == "weak" else max(1, B // world)
@@ -250,6 +373,8 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the committed ncu --set full capture "
+                                  "(profiles/traffic.json); DRAM counters cannot be read outside the profiler",
                 "algorithmic_bytes_per_launch": (BYTES_WRITE if dom == "cache_write3_kernel" else BYTES_READ) * scale,
                 "frac_of_nominal_8TBps": kern[dom]["gbs"] / 8000.0}
 
@@ -279,8 +404,15 @@ def run_ours(args):
     be = ECCBackend(images[0], cfg, HQ)
     kh = torch.empty(k.shape, dtype=k.dtype, pin_memory=True).copy_(k)
     vh = torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v)
+    ko_host = torch.empty(k_out.shape, dtype=k_out.dtype, pin_memory=True)     # the dequantised K / V come back to the host
+    vo_host = torch.empty(v_out.shape, dtype=v_out.dtype, pin_memory=True)
     ctr_host = torch.empty(_lib.NCOUNTERS, dtype=torch.int64, pin_memory=True)
     n_e2e = max(2, min(K, 10))
+    d2h_stream = torch.cuda.Stream(dev)                  # PCIe is full duplex: the read-back overlaps the next step's upload
+    ko2 = [k_out, torch.empty_like(k_out)]
+    vo2 = [v_out, torch.empty_like(v_out)]
+    out_ready = [torch.cuda.Event() for _ in range(2)]
+    out_copied = [torch.cuda.Event() for _ in range(2)]
 
     # double-buffered device inputs on a copy stream: the H2D of step i+1 runs while the kernels of step i do (the step is
     # PCIe-bound: 537 MB in, 0.37 ms of kernels)
@@ -304,9 +436,16 @@ def run_ours(args):
         stream.wait_event(copied[b])
         be.write(kd2[b], vd2[b], 0, seq_id=0)
         consumed[b].record(stream)
+        stream.wait_event(out_copied[b])                 # the read-back that last used this output pair has finished
         read_cache(images[0].k_cache, images[0].v_cache, images[0].k_scales, images[0].v_scales, images[0].block_table, cl, 0, BS, D,
-                   CODEC, use_interpolation=True, out_dtype=torch.float16, counters=be._counters, max_context=S, out=(k_out, v_out))
-        ctr_host.copy_(be._counters, non_blocking=True)
+                   CODEC, use_interpolation=True, out_dtype=torch.float16, counters=be._counters, max_context=S, out=(ko2[b], vo2[b]))
+        out_ready[b].record(stream)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(out_ready[b])
+            ko_host.copy_(ko2[b], non_blocking=True)
+            vo_host.copy_(vo2[b], non_blocking=True)
+            ctr_host.copy_(be._counters, non_blocking=True)
+            out_copied[b].record(d2h_stream)
 
     # append-mode bookkeeping of the manager: the blocks are already mapped by the benchmark's own block table
     images[0].seq_to_blocks = {b: images[0].block_table[b].tolist() for b in range(b_local)}
@@ -319,14 +458,24 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(n_e2e):
         e2e_step()
+    stream.wait_stream(d2h_stream)                       # the timed region ends when the last result is on the host
     e1.record(stream)
     torch.cuda.synchronize(dev)
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), dev)
     e2e = {"value": world * n_e2e * BYTES_STEP * scale / (e2e_ms * 1e-3) / 1e9, "unit": UNIT,
-           "h2d_bytes_per_step": int(2 * k.numel() * k.element_size()), "d2h_bytes_per_step": int(ctr_host.numel() * 8),
-           "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
-           "api": "ECCBackend.write + kv_cache.read_cache from pinned host fp16 K/V, inputs double-buffered on a copy stream; "
-                  "result read back = counter vector"}
+           "h2d_bytes_per_step": int(2 * k.numel() * k.element_size()),
+           "d2h_bytes_per_step": int(2 * k_out.numel() * k_out.element_size() + ctr_host.numel() * 8),
+           "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e, "cpu_affinity": affinity,
+           "api": "ECCBackend.write + kv_cache.read_cache from pinned host fp16 K/V, inputs double-buffered on a copy stream; the "
+                  "dequantised K/V (fp16) and the counter vector are read back to pinned host memory on a third stream"}
+
+    # ---------------- config 1 (BASELINE.json configs[0]) on the GPU: three flat kernels, GPT-2 KV shape
+    c1 = None
+    if not args.no_attention:
+        try:
+            c1 = gpu_c1(torch, dev, lib, _lib, peak)
+        except Exception as exc:
+            c1 = {"error": repr(exc)}
 
     # ---------------- secondary metric: ECC-fused paged decode attention, C5 per-GPU shard (batch 8 x 32k context)
     attn = None
@@ -346,8 +495,20 @@ def run_ours(args):
         except Exception as exc:
             golay = {"error": repr(exc)}
 
+    # ---------------- the reference's own Triton kernels on this GPU (rank 0, single-GPU runs; tools/ref_triton_bench.py)
+    ref_triton = None
+    if rank == 0 and world == 1 and not args.no_attention and not args.no_triton:
+        try:
+            from tools.ref_triton_bench import run as ref_triton_run
+            ref_triton = ref_triton_run(ctx=8192)
+        except Exception as exc:
+            ref_triton = {"error": repr(exc)}
+
     if rank == 0:
-        cb = cpu_leg(3, 1, min_seconds=10.0) if not args.no_cpu else None   # ~10 s of host work
+        cb = None
+        if not args.no_cpu:
+            cb = cpu_leg(3, 1, min_seconds=8.0)   # ~8 s of host work
+            cb["c1"] = cpu_c1()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic",
@@ -359,7 +520,7 @@ def run_ours(args):
                 "roofline": roofline, "kernels": kern, "write_kernel_ber_sweep": ber_sweep, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": 2 * K,
                 "clocks": sampler.report(),
                 "counters": {"corrected": stats[0], "detected": stats[1], "bits_flipped": stats[2], "interpolated": stats[5]},
-                "decode_attention": attn, "golay_c4": golay}
+                "c1": c1, "decode_attention": attn, "golay_c4": golay, "reference_triton": ref_triton}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
@@ -404,7 +565,8 @@ def bench_attention(torch, dev, lib, _lib, paged_attention_ecc, SimpleBlockManag
             "ms_per_layer_call": ms, "context_tokens_per_s_per_gpu": Bq * ctx / (ms * 1e-3),
             "context_tokens_per_s_all_gpus": world * Bq * ctx / (ms * 1e-3),
             "generated_tokens_per_s_32_layers": world * Bq / (32 * ms * 1e-3), "gbs": nbytes / (ms * 1e-3) / 1e9,
-            "roofline_frac": nbytes / (ms * 1e-3) / 1e9 / peak, "kernel": "attn_mma_kernel (ECC decode in the K/V prologue, mma.sync m16n8k16) + attn_merge_kernel"}
+            "roofline_frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+            "kernel": "attn_tc_kernel (TMA gather4 page loads, in-place SWAR ECC decode, tcgen05.mma kind::i8 into TMEM) + attn_merge_kernel"}
 
 
 def bench_golay_c4(torch, dev, lib, _lib, SimpleBlockManager, world):
@@ -461,6 +623,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-attention", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-triton", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -534,10 +534,12 @@ def attention_prefill(q, k_float, v_float, num_kv_groups, causal):
 
 
 def paged_decode_attention(query, cache: PagedCache, block_table, context_lens, layer, sm_scale=None,
-                           use_interpolation=False, v_use_k_scales=False):
+                           use_interpolation=False, v_use_k_scales=False, precision=np.float32):
     """reference_attention_ecc (attention_ecc.py:783-909) generalised to GQA (kv_head = q_head //
     group) and to separate K/V scales (Q15). query [B,Hq,D] -> fp32 [B,Hq,D]; an empty
-    context yields zeros (Q14). Also returns (corrected, detected) summed over K and V."""
+    context yields zeros (Q14). Also returns (corrected, detected) summed over K and V.
+    precision=np.float64 evaluates the same formula (fp32 dequantised K/V, as the reference has them) with float64
+    products and sums: the yardstick for contexts long enough that fp32 summation order shows at the 1e-4 level."""
     query = np.asarray(query).astype(np.float32)
     B, Hq, D = query.shape
     g = Hq // cache.H
@@ -558,9 +560,9 @@ def paged_decode_attention(query, cache: PagedCache, block_table, context_lens, 
         det += d1 + d2
         kf = dequantize_int4(kd, ks)
         vf = dequantize_int4(vd, ks if v_use_k_scales else vs)
-        kf = np.repeat(kf, g, axis=1).transpose(1, 0, 2)
-        vf = np.repeat(vf, g, axis=1).transpose(1, 0, 2)
-        s = np.einsum("hd,hcd->hc", query[b], kf) * np.float32(sm_scale)
+        kf = np.repeat(kf, g, axis=1).transpose(1, 0, 2).astype(precision)
+        vf = np.repeat(vf, g, axis=1).transpose(1, 0, 2).astype(precision)
+        s = np.einsum("hd,hcd->hc", query[b].astype(precision), kf) * precision(sm_scale)
         s = s - s.max(axis=-1, keepdims=True)
         p = np.exp(s)
         p = p / p.sum(axis=-1, keepdims=True)

@@ -446,6 +446,8 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
           tc_commit(&mi.oready[b]);
           tc_commit(&mi.empty[s]);       // every MMA that reads this stage has completed (S(n) was consumed before W(n) existed)
         }
+        // the commits arrive asynchronously: see the last ones land before this CTA's shared memory is given up
+        for (int back = min(c.n, kStages); back > 0; --back) mbar_wait(&mi.empty[(c.n - back) % kStages], ((c.n - back) / kStages) & 1);
       }
     }
   } else if (warp >= 4 && warp < 4 + kSoftmaxWarps) {
@@ -484,11 +486,14 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       // maxima nor the weight scale move -- after the first tile of an item that is almost always -- so the steady state of a
       // tile is: read S, one barrier-with-OR ("does anyone exceed the running maximum?"), exponentials, one 8-byte store.
       // Lazy rescaling: the running maximum only moves when a score exceeds it by more than kSlack (base-2 units), so weights
-      // may reach 2^kSlack; the fixed-point format keeps 8 bits of headroom for that and 24 bits below one.  (With an exact
-      // running maximum every other tile of a 16-tile item set a new record for one of the four heads.)  A finite sentinel
-      // instead of -inf keeps the arithmetic free of special cases.
+      // may reach 2^kSlack; the 32-bit fixed-point format keeps kSlackBits of headroom for that and 28 bits below one.  (With
+      // an exact running maximum every other tile of a 16-tile item set a new record for one of the four heads.)  The
+      // headroom is paid in precision: every token's weight is rounded to the format's LSB, and over a 9 000-token context
+      // those roundings add up like sqrt(N) -- 8 bits of headroom measured 7e-5 against a float64 evaluation, 4 bits 3e-6.
+      // A finite sentinel instead of -inf keeps the arithmetic free of special cases.
       constexpr float kNegBig = -1.0e30f;
-      constexpr float kSlack = 8.0f;
+      constexpr int kSlackBits = 4;
+      constexpr float kSlack = (float)kSlackBits;
       float m_run[2], l_thr[2], lw_thr[2], oacc[2];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) { m_run[hh] = kNegBig; l_thr[hh] = 0.0f; lw_thr[hh] = 0.0f; oacc[hh] = 0.0f; }
@@ -570,21 +575,21 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
             lw_thr[hh] *= al;
             oacc[hh] *= al;
           }
-          // weights p * vs < 2^(kSlack + E) (E - 1 = exponent bound of the v scales) as 32-bit fixed point:
-          // wscale = 2^(24 - E), sigma = 1 / wscale
-          eb_run = max(eb_run, min(max(__float_as_uint(vsmax) >> 23, 24u), 254u));
-          wscale = __uint_as_float((277u - eb_run) << 23);
-          sigma = __uint_as_float((eb_run - 23u) << 23);
+          // weights p * vs < 2^(kSlackBits + E) (E - 1 = exponent bound of the v scales) as 32-bit fixed point:
+          // wscale = 2^(32 - kSlackBits - E), sigma = 1 / wscale
+          eb_run = max(eb_run, min(max(__float_as_uint(vsmax) >> 23, 32u - kSlackBits), 254u));
+          wscale = __uint_as_float((285u - kSlackBits - eb_run) << 23);
+          sigma = __uint_as_float((eb_run - 31u + kSlackBits) << 23);
           fresh = true;
         }
         uint32_t wfix[2];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const float p = valid ? exp2f(sc[hh] - m_run[hh]) : 0.0f;
-          const float pw = p * vs;
           l_thr[hh] += p;
-          lw_thr[hh] += pw;
-          wfix[hh] = __float2uint_rn(pw * wscale);
+          wfix[hh] = __float2uint_rn(p * vs * wscale);
+          // the "-8" term uses the weight the tensor core sees, so a weight's rounding error multiplies (nibble - 8), not the nibble
+          lw_thr[hh] = fmaf(__uint2float_rn(wfix[hh]), sigma, lw_thr[hh]);
         }
         *reinterpret_cast<uint2*>(sm + kOffW + b * kWBytes + r * 16 + g * 8) = make_uint2(wfix[0], wfix[1]);
         if (r == 0 && g == 0) mi.pv_fresh[b] = fresh ? 1u : 0u;

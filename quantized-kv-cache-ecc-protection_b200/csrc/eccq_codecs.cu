@@ -4,7 +4,7 @@
 // Every kernel is HBM-bound byte/integer work: 128-bit coalesced loads/stores of packed codewords, a grid sized as a
 // multiple of the SM count with a grid-stride loop, several independent 16-byte loads in flight per thread, and
 // block-level counters (one atomicAdd per CTA).  Replaces the Triton kernels K1-K12 of SURVEY.md section 2.1.
-#include "eccq_internal.h"
+#include "eccq_cache_geom.cuh"   // FastDiv
 
 namespace eccq {
 
@@ -409,10 +409,12 @@ __global__ void __launch_bounds__(kThreads) inject_fast2_kernel(const uint8_t* _
 
 // ------------------------------------------------------------------------------------------------ interpolation
 // [outer, len, inner] view; neighbours at +-inner. VEC: inner % 16 == 0 and 16-byte aligned bases.
-template <bool VEC>
+// FAST32: fewer than 2^31 16-byte chunks, so the token index comes from two multiply-shift divisions instead of two 64-bit
+// divisions per chunk (the 64-bit ones cost more than the rest of the kernel).
+template <bool VEC, bool FAST32>
 __global__ void __launch_bounds__(kThreads) interpolate_kernel(const uint8_t* __restrict__ q, const uint8_t* __restrict__ et,
                                                                 uint8_t* __restrict__ out, int64_t outer, int64_t len,
-                                                                int64_t inner) {
+                                                                int64_t inner, FastDiv div_inner16, FastDiv div_len) {
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = outer * len * inner;
@@ -421,7 +423,13 @@ __global__ void __launch_bounds__(kThreads) interpolate_kernel(const uint8_t* __
     const int64_t n16 = total >> 4;
     const int64_t inner16 = inner >> 4;
     for (int64_t i = tid; i < n16; i += nthreads) {
-      const int64_t t = (i / inner16) % len;
+      int64_t t;
+      if (FAST32) {
+        const uint32_t row = div_inner16.div((uint32_t)i);
+        t = (int64_t)(row - div_len.div(row) * (uint32_t)len);
+      } else {
+        t = (i / inner16) % len;
+      }
       const uint4 v = ld_stream(q + (i << 4));
       const uint4 e = ld_stream(et + (i << 4));
       uint32_t vv[4] = {v.x, v.y, v.z, v.w};
@@ -436,22 +444,31 @@ __global__ void __launch_bounds__(kThreads) interpolate_kernel(const uint8_t* __
         any |= dbl[k];
       }
       // saturate: any byte > 15 -> 15
+      uint32_t big = (vv[0] | vv[1] | vv[2] | vv[3]) & 0xF0F0F0F0u;
+      if (big) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t hi = vv[k] & 0xF0F0F0F0u; hi |= hi >> 1; hi |= hi >> 2; hi = (hi >> 4) & M01;  // 1 where byte > 15
-        vv[k] = (vv[k] & ~spread8(hi)) | (spread8(hi) & M0F);
+        for (int k = 0; k < 4; ++k) {
+          uint32_t hi = vv[k] & 0xF0F0F0F0u; hi |= hi >> 1; hi |= hi >> 2; hi = (hi >> 4) & M01;  // 1 where byte > 15
+          vv[k] = (vv[k] & ~spread8(hi)) | (spread8(hi) & M0F);
+        }
       }
       if (any) {
         const int64_t il = (t > 0) ? i - inner16 : i;
         const int64_t ir = (t + 1 < len) ? i + inner16 : i;
-        const uint4 l = ld_stream(q + (il << 4)), r = ld_stream(q + (ir << 4));
+        const uint4 l = __ldg(reinterpret_cast<const uint4*>(q + (il << 4))), r = __ldg(reinterpret_cast<const uint4*>(q + (ir << 4)));
         const uint32_t ll[4] = {l.x, l.y, l.z, l.w}, rr[4] = {r.x, r.y, r.z, r.w};
-        const uint8_t* lb = reinterpret_cast<const uint8_t*>(ll);
-        const uint8_t* rb = reinterpret_cast<const uint8_t*>(rr);
-        uint8_t* ob = reinterpret_cast<uint8_t*>(vv);
-        const uint8_t* db = reinterpret_cast<const uint8_t*>(dbl);
-        for (int b = 0; b < 16; ++b)
-          if (db[b]) { const uint32_t s = ((uint32_t)lb[b] + rb[b] + 1u) >> 1; ob[b] = (uint8_t)min(s, 15u); }
+        if (((l.x | l.y | l.z | l.w | r.x | r.y | r.z | r.w) & 0xF0F0F0F0u) == 0) {
+          // neighbours are INT4 codes (the only case the cache path produces): SWAR average, no byte loop
+#pragma unroll
+          for (int k = 0; k < 4; ++k) vv[k] = interp4(vv[k], ll[k], rr[k], dbl[k]);
+        } else {
+          const uint8_t* lb = reinterpret_cast<const uint8_t*>(ll);
+          const uint8_t* rb = reinterpret_cast<const uint8_t*>(rr);
+          uint8_t* ob = reinterpret_cast<uint8_t*>(vv);
+          const uint8_t* db = reinterpret_cast<const uint8_t*>(dbl);
+          for (int b = 0; b < 16; ++b)
+            if (db[b]) { const uint32_t s = ((uint32_t)lb[b] + rb[b] + 1u) >> 1; ob[b] = (uint8_t)min(s, 15u); }
+        }
       }
       st_stream(out + (i << 4), make_uint4(vv[0], vv[1], vv[2], vv[3]));
     }
@@ -465,6 +482,55 @@ __global__ void __launch_bounds__(kThreads) interpolate_kernel(const uint8_t* __
       }
       out[i] = (uint8_t)min(v, 15u);
     }
+  }
+}
+
+// inner == 1 (interpolation along the contiguous axis, the reference's 1-D / 2-D case) with len % 16 == 0: a lane owns 16
+// consecutive positions of one row; the neighbour streams are the chunk shifted by one byte, completed by the byte before /
+// after the chunk (index-clamped at the row ends).
+__global__ void __launch_bounds__(kThreads) interpolate_rows_kernel(const uint8_t* __restrict__ q, const uint8_t* __restrict__ et,
+                                                                     uint8_t* __restrict__ out, int64_t n16, FastDiv div_len16, uint32_t len16) {
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += nthreads) {
+    const uint4 v = ld_stream(q + (i << 4));
+    const uint4 e = ld_stream(et + (i << 4));
+    uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+    const uint32_t ee[4] = {e.x, e.y, e.z, e.w};
+    uint32_t dbl[4], any = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t x = ee[k] ^ 0x02020202u;
+      uint32_t z = x | (x >> 4); z |= z >> 2; z |= z >> 1;
+      dbl[k] = ~z & M01;
+      any |= dbl[k];
+    }
+    if (any) {
+      const uint32_t c = (uint32_t)i - div_len16.div((uint32_t)i) * len16;      // chunk index inside the row
+      const uint32_t prev = c > 0 ? (uint32_t)__ldg(q + (i << 4) - 1) : (v.x & 0xFFu);
+      const uint32_t next = c + 1 < len16 ? (uint32_t)__ldg(q + (i << 4) + 16) : (v.w >> 24);
+      const uint32_t ll[4] = {(v.x << 8) | prev, __funnelshift_l(v.x, v.y, 8), __funnelshift_l(v.y, v.z, 8), __funnelshift_l(v.z, v.w, 8)};
+      const uint32_t rr[4] = {__funnelshift_r(v.x, v.y, 8), __funnelshift_r(v.y, v.z, 8), __funnelshift_r(v.z, v.w, 8), (v.w >> 8) | (next << 24)};
+      if (((v.x | v.y | v.z | v.w | (prev << 4) | (next << 4)) & 0xF0F0F0F0u) == 0 && prev < 16u && next < 16u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vv[k] = interp4(vv[k], ll[k], rr[k], dbl[k]);
+      } else {
+        const uint8_t* lb = reinterpret_cast<const uint8_t*>(ll);
+        const uint8_t* rb = reinterpret_cast<const uint8_t*>(rr);
+        uint8_t* ob = reinterpret_cast<uint8_t*>(vv);
+        const uint8_t* db = reinterpret_cast<const uint8_t*>(dbl);
+        for (int b = 0; b < 16; ++b)
+          if (db[b]) { const uint32_t s2 = ((uint32_t)lb[b] + rb[b] + 1u) >> 1; ob[b] = (uint8_t)s2; }
+      }
+    }
+    // every output is clamp(v + 0.5, 0, 15) truncated: values above 15 saturate
+    if ((vv[0] | vv[1] | vv[2] | vv[3]) & 0xF0F0F0F0u) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t hi = vv[k] & 0xF0F0F0F0u; hi |= hi >> 1; hi |= hi >> 2; hi = (hi >> 4) & M01;
+        vv[k] = (vv[k] & ~spread8(hi)) | (spread8(hi) & M0F);
+      }
+    }
+    st_stream(out + (i << 4), make_uint4(vv[0], vv[1], vv[2], vv[3]));
   }
 }
 
@@ -617,9 +683,18 @@ extern "C" int eccq_interpolate(const uint8_t* q, const uint8_t* etype, uint8_t*
   if (total == 0) return ECCQ_OK;
   if (!q || !etype || !out) return fail(ECCQ_EINVAL, "interpolate: null pointer");
   const bool vec = (inner % 16 == 0) && aligned16(q) && aligned16(etype) && aligned16(out);
-  if (vec)
-    interpolate_kernel<true><<<grid_for(total, kThreads * 16), kThreads, 0, (cudaStream_t)stream>>>(q, etype, out, outer, len, inner);
+  if (inner == 1 && len % 16 == 0 && (total >> 4) < 0x7FFFFFFFll && aligned16(q) && aligned16(etype) && aligned16(out)) {
+    const uint32_t len16 = (uint32_t)(len >> 4);
+    interpolate_rows_kernel<<<grid_for(total, kThreads * 16), kThreads, 0, (cudaStream_t)stream>>>(q, etype, out, total >> 4, FastDiv::make(len16), len16);
+    return check_launch("interpolate");
+  }
+  const FastDiv d16 = FastDiv::make((uint32_t)std::max<int64_t>(1, std::min<int64_t>(inner >> 4, 0x7FFFFFFF)));
+  const FastDiv dl = FastDiv::make((uint32_t)std::max<int64_t>(1, std::min<int64_t>(len, 0x7FFFFFFF)));
+  if (vec && (total >> 4) < 0x7FFFFFFFll && len < 0x7FFFFFFFll)
+    interpolate_kernel<true, true><<<grid_for(total, kThreads * 16), kThreads, 0, (cudaStream_t)stream>>>(q, etype, out, outer, len, inner, d16, dl);
+  else if (vec)
+    interpolate_kernel<true, false><<<grid_for(total, kThreads * 16), kThreads, 0, (cudaStream_t)stream>>>(q, etype, out, outer, len, inner, d16, dl);
   else
-    interpolate_kernel<false><<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(q, etype, out, outer, len, inner);
+    interpolate_kernel<false, false><<<grid_for(total, kThreads), kThreads, 0, (cudaStream_t)stream>>>(q, etype, out, outer, len, inner, d16, dl);
   return check_launch("interpolate");
 }
