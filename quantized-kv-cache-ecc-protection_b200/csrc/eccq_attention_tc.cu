@@ -19,8 +19,7 @@
 //               128-token stages (complete_tx on the stage's "full" barrier)
 //   warp 1      MMA issuer (one thread): 4 + 4 tcgen05.mma per tile, tcgen05.commit to the barriers that hand S / O to the
 //               softmax warps and the stage back to the producer
-//   warp 2      TMEM allocation; query preparation for the next (sequence, kv-head, split) item: digits + constants,
-//               double buffered
+//   warp 2      TMEM allocation
 //   warps 4-7   softmax: thread = token (TMEM lane) for S, thread = dim for O; online softmax in base 2, fp32 state
 //   warps 8..   decode: LDS.128 raw codewords -> SWAR syndrome decode (eccq_common.cuh) -> STS.128 corrected nibbles IN PLACE
 //               at the 128-byte-swizzled position the UMMA descriptors expect
@@ -42,6 +41,9 @@ constexpr int kWBytes = kTile * 16;        // [token][16 weight bytes]
 constexpr int kFrontWarps = 12;            // roles 0-11: producer, S issuer, query/TMEM, PV issuer, 8 softmax
 constexpr int kSoftmaxWarps = 8;
 constexpr int kSoftmaxThreads = kSoftmaxWarps * 32;
+#ifndef ECCQ_TC_GROUPWAIT
+#define ECCQ_TC_GROUPWAIT 0
+#endif
 #ifndef ECCQ_TC_REVERSE_ROLES
 #define ECCQ_TC_REVERSE_ROLES 1            // roles are numbered from the LAST warp down: the issue arbiter favours high warp ids, and
 #endif                                     // the latency-critical roles (issuers, softmax, producers) should win over the decode warps
@@ -52,17 +54,19 @@ constexpr uint32_t kSpinLimit = 1u << 24;   // x 4 probes, each sleeping up to t
 // ---- shared-memory map (offsets from a 1024-byte aligned base) -------------------------------------------------------
 constexpr int kOffStages = 0;
 constexpr int kOffQop = kOffStages + kStages * kStageBytes;
-constexpr int kOffW = kOffQop + 2 * kQopBytes;
+constexpr int kQBufs = 3;                  // query-digit buffers: item i+2 is prepared while items i and i+1 are in flight
+constexpr int kOffW = kOffQop + kQBufs * kQopBytes;
 constexpr int kOffMisc = kOffW + 2 * kWBytes;
 struct Misc {
   uint64_t full[kStages], kdec[kStages], vdec[kStages], empty[kStages];
-  uint64_t sready[2], sfree[2], wready[2], oready[2], qready[2], qfree[2];
-  float qscale[2][kHeadsPerPass];        // 2^(e-27) * sm_scale * log2(e) per head (0 for unused heads)
-  int32_t qc01[2][kHeadsPerPass];        // 8 * sum_d (d0*128 + d1)
-  int32_t qc23[2][kHeadsPerPass];        // 8 * sum_d (d2*128 + d3)
-  float red[2][kSoftmaxWarps][4];        // rare-path exchange of the softmax warps: max score of the 2 heads, max v scale
-  float fin[kSoftmaxWarps][4];           // end-of-item reduction: l and sum(w) of the 2 heads per warp
+  uint64_t sready[2], sfree[2], wready[2], oready[2], qready[kQBufs];
+  float qscale[kQBufs][kHeadsPerPass];        // 2^(e-27) * sm_scale * log2(e) per head (0 for unused heads)
+  int32_t qc01[kQBufs][kHeadsPerPass];        // 8 * sum_d (d0*128 + d1)
+  int32_t qc23[kQBufs][kHeadsPerPass];        // 8 * sum_d (d2*128 + d3)
+  alignas(16) float red[2][kSoftmaxWarps][4];        // rare-path exchange of the softmax warps: max score of the 2 heads, max v scale
+  alignas(16) float fin[kSoftmaxWarps][4];           // end-of-item reduction: l and sum(w) of the 2 heads per warp
   uint32_t page_mask[kStages];           // bit j: page j of the stage's tile was loaded
+  alignas(16) int32_t rowtab[2][128];                // per producer: [2 segments][32] gather rows, then [2][32] pages (scale rows)
   uint32_t pv_fresh[2];                  // 1: PV of this weight buffer starts a new accumulation in TMEM (written before wready)
   uint32_t tmem_base;
 };
@@ -251,9 +255,8 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       mbar_init(&mi.sfree[b], kSoftmaxThreads);
       mbar_init(&mi.wready[b], kSoftmaxThreads);
       mbar_init(&mi.oready[b], 1);
-      mbar_init(&mi.qready[b], 1);
-      mbar_init(&mi.qfree[b], kSoftmaxThreads);
     }
+    for (int b = 0; b < kQBufs; ++b) mbar_init(&mi.qready[b], 4);   // one arrival per preparing warp (= per q-head of the pass)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -266,136 +269,89 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
   const uint32_t tmem = mi.tmem_base;   // columns [0,32): two S buffers, [32,48): the O accumulator
 
   if (warp == 0 || warp == 2) {
-    // =============================================================== producers: role 0 = K codewords + K scales (and the
-    // query digits of every new item), role 2 = V codewords + V scales
+    // =============================================================== producers: role 0 = K codewords + K scales, role 2 = V
     // TMA tile::gather4: the four row coordinates of one instruction are four pages straight from the block table, so a
     // 128-token tile is 2 instructions for the codewords and 1-2 for the scales per producer (a plain cp.async.bulk per page
-    // costs ~100 cycles of issue latency each -- 32 per tile made the producer the bottleneck; so did ONE warp issuing all 8
-    // gathers of a tile: ~2400 cycles per tile).  Pages that are unmapped or past the context are replaced by row 0 (loaded,
-    // then masked through page_mask), which keeps the byte count per stage constant.  The block-table entries of the NEXT
-    // tile are fetched before this tile's copies are issued.
+    // costs ~100 cycles of issue latency each -- 32 per tile made the producer the bottleneck).  Every warp of the CTA gets
+    // about the same share of issue slots, so the producer's own instruction count per tile bounds the tile period: the
+    // block table is therefore resolved for FOUR tiles at a time (one entry per lane, one coalesced load, the next segment's
+    // entries fetched before this segment's copies go out) into a small row table in shared memory, and the per-tile work of
+    // the issuing lane is two 16-byte reads of that table, the stage's barrier and the gathers.  Pages that are unmapped or
+    // past the context are replaced by row 0 (loaded, then masked through page_mask), which keeps the byte count per stage
+    // constant.
     const int part = warp == 0 ? 0 : 1;
     const CUtensorMap* tm_c = part ? &a.tm_v : &a.tm_k;
     const CUtensorMap* tm_s = part ? &a.tm_vs : &a.tm_ks;
     const float* scales = part ? a.vscales : a.g.k_scales;
     const int spp = bs >> 4;                        // 2048-byte rows per page
     const int lgspp = lgbs - 4;
-    const int lh0 = a.layer * a.g.H;
-    TileCursor c;
-    c.item = blockIdx.x;
-    cursor_seek(a, nitems, c);
-    auto fetch = [&](const TileCursor& tc_) -> int {
-      if (!tc_.valid) return -1;
-      const int tok0 = (tc_.it.tile0 + tc_.t) * kTile + lane * bs;
-      const int lb = tok0 >> lgbs;
-      return (lane < ppt && tok0 < tc_.it.c1 && lb < a.max_blocks) ? a.block_table[(int64_t)tc_.it.seq * a.max_blocks + lb] : -1;
+    const int lh0 = a.layer * a.g.H, LH = a.g.L * a.g.H;
+    const int tl = lane >> 3, pj = lane & 7;        // this lane's tile within the segment, page / row slot within the tile
+    int32_t* rowtab = mi.rowtab[part];              // [2 segments][32]: 2048-byte rows; [2][32] after it: pages (scale rows)
+    struct Seg { int item, t0, nt; Item it; bool valid; };
+    auto seg_first = [&](Seg& sg, int item) {       // first segment of the next non-empty item at or after `item`
+      sg.item = item;
+      while (sg.item < nitems && !get_item(a, sg.item, sg.it)) sg.item += gridDim.x;
+      sg.valid = sg.item < nitems;
+      sg.t0 = 0;
+      sg.nt = sg.valid ? min(4, sg.it.ntiles) : 0;
     };
-    int blk = fetch(c);
-    int j = 0;                                      // non-empty items started (query buffer = j & 1)
-    for (int n = 0; c.valid; ++n) {
-      const int kvh = c.it.kvh;
-      const bool new_item = c.t == 0;
-      const Item it = c.it;
-      TileCursor nx = c;
-      cursor_next(a, nitems, nx);
+    auto seg_next = [&](Seg& sg) {
+      if (sg.t0 + sg.nt < sg.it.ntiles) { sg.t0 += sg.nt; sg.nt = min(4, sg.it.ntiles - sg.t0); }
+      else seg_first(sg, sg.item + gridDim.x);
+    };
+    auto fetch = [&](const Seg& sg) -> int {
+      if (!sg.valid || tl >= sg.nt || pj >= ppt) return -1;
+      const int tok0 = (sg.it.tile0 + sg.t0 + tl) * kTile + pj * bs;
+      const int lb = tok0 >> lgbs;
+      return (tok0 < sg.it.c1 && lb < a.max_blocks) ? a.block_table[(int64_t)sg.it.seq * a.max_blocks + lb] : -1;
+    };
+    Seg sg;
+    seg_first(sg, blockIdx.x);
+    int blk = fetch(sg);
+    int n = 0, segno = 0;                           // tiles issued, segments
+    while (sg.valid) {
+      Seg nx = sg;
+      seg_next(nx);
       const int blk_next = fetch(nx);
-      const uint32_t vm = __ballot_sync(0xFFFFFFFFu, blk >= 0);
-      const int page = blk >= 0 ? blk * (a.g.L * a.g.H) + lh0 + kvh : 0;           // lane j < ppt: page of the tile's j-th block
-      // lane j < 8: 2048-byte row j of the tile = sub-row (j % spp) of page (j / spp)
-      const int row = spp == 1 ? page : (__shfl_sync(0xFFFFFFFFu, page, (lane & 7) >> lgspp) << lgspp) + (lane & (spp - 1));
-      const int r0 = __shfl_sync(0xFFFFFFFFu, row, 0), r1 = __shfl_sync(0xFFFFFFFFu, row, 1), r2 = __shfl_sync(0xFFFFFFFFu, row, 2),
-                r3 = __shfl_sync(0xFFFFFFFFu, row, 3), r4 = __shfl_sync(0xFFFFFFFFu, row, 4), r5 = __shfl_sync(0xFFFFFFFFu, row, 5),
-                r6 = __shfl_sync(0xFFFFFFFFu, row, 6), r7 = __shfl_sync(0xFFFFFFFFu, row, 7);
-      int p0 = r0, p1 = r1, p2 = r2, p3 = r3;
-      if (spp != 1) { p0 = __shfl_sync(0xFFFFFFFFu, page, 0); p1 = __shfl_sync(0xFFFFFFFFu, page, 1); p2 = __shfl_sync(0xFFFFFFFFu, page, 2); p3 = __shfl_sync(0xFFFFFFFFu, page, 3); }
-      const int s = n % kStages;
-      unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
-      if (lane == 0) {
-        mbar_wait(&mi.empty[s], ((n / kStages) & 1) ^ 1);
-        TC_TRACE(n, part ? EV_LOAD_V : EV_LOAD_ISSUE);
-        if (part == 0) mi.page_mask[s] = vm;
-        mbar_arrive_tx(&mi.full[s], (uint32_t)(kPartBytes + kTile * 4));
-        tma_gather4(st + part * kPartBytes, tm_c, r0, r1, r2, r3, &mi.full[s]);
-        tma_gather4(st + part * kPartBytes + 8192, tm_c, r4, r5, r6, r7, &mi.full[s]);
-        unsigned char* sdst = st + 2 * kPartBytes + part * kTile * 4;
-        if (ppt == 8) {
-          tma_gather4(sdst, tm_s, r0, r1, r2, r3, &mi.full[s]);
-          tma_gather4(sdst + 256, tm_s, r4, r5, r6, r7, &mi.full[s]);
-        } else if (ppt == 4) {
-          tma_gather4(sdst, tm_s, p0, p1, p2, p3, &mi.full[s]);
-        } else {
-          bulk_g2s(sdst, scales + (int64_t)p0 * bs, (uint32_t)(bs * 4), &mi.full[s]);
-          if (ppt == 2) bulk_g2s(sdst + bs * 4, scales + (int64_t)p1 * bs, (uint32_t)(bs * 4), &mi.full[s]);
-        }
-      }
+      const uint32_t vm32 = __ballot_sync(0xFFFFFFFFu, blk >= 0);
+      const int page = blk >= 0 ? blk * LH + lh0 + sg.it.kvh : 0;
+      // lane (tile, j): 2048-byte row j of the tile = sub-row (j % spp) of page (j / spp) of that tile
+      const int row = spp == 1 ? page : (__shfl_sync(0xFFFFFFFFu, page, (lane & ~7) | (pj >> lgspp)) << lgspp) + (pj & (spp - 1));
+      int32_t* rt = rowtab + (segno & 1) * 32;
+      rt[lane] = row;
+      rt[64 + lane] = page;
       __syncwarp();
-      if (part == 0 && new_item) {
-        // ---- query digits of the item whose first tile was just requested (the loads run ~4 tiles ahead of the MMAs)
-        const int qb = j & 1;
-        mbar_wait(&mi.qfree[qb], ((j >> 1) & 1) ^ 1);
-        const int hh = lane >> 3, c = lane & 7;               // head of the pass, 16-dim chunk
-        const int g0 = it.pass * kHeadsPerPass;
-        const bool used = g0 + hh < G;
-        float v[16];
-        float amax = 0.0f;
-        const int64_t qbase = ((int64_t)it.seq * a.Hq + (int64_t)it.kvh * G + g0 + hh) * kD + c * 16;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          v[e] = used ? load_q(a.q, a.q_dtype, qbase + e) : 0.0f;
-          amax = fmaxf(amax, fabsf(v[e]));
-        }
-        amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 1));
-        amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 2));
-        amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, 4));
-        // amax = m * 2^ex with m in [0.5, 1): |q| * 2^(27-ex) < 2^27
-        int ex = 0;
-        if (amax > 0.0f && amax < INFINITY) (void)frexpf(amax, &ex);
-        const float up = ldexpf(1.0f, 27 - ex);
-        uint32_t dig[4][4];   // [digit][word of 4 dims]
-        int32_t s01 = 0, s23 = 0;
-#pragma unroll
-        for (int w4 = 0; w4 < 4; ++w4) {
-          uint32_t pk[4] = {0, 0, 0, 0};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            int32_t x = __float2int_rn(v[w4 * 4 + e] * up);
-            const int32_t d3 = ((x + 64) & 127) - 64; x = (x - d3) >> 7;
-            const int32_t d2 = ((x + 64) & 127) - 64; x = (x - d2) >> 7;
-            const int32_t d1 = ((x + 64) & 127) - 64; x = (x - d1) >> 7;
-            const int32_t d0 = x;
-            s01 += d0 * 128 + d1;
-            s23 += d2 * 128 + d3;
-            pk[0] |= (uint32_t)(d0 & 0xFF) << (8 * e);
-            pk[1] |= (uint32_t)(d1 & 0xFF) << (8 * e);
-            pk[2] |= (uint32_t)(d2 & 0xFF) << (8 * e);
-            pk[3] |= (uint32_t)(d3 & 0xFF) << (8 * e);
+      if (lane == 0) {
+        for (int ti = 0; ti < sg.nt; ++ti, ++n) {
+          const int s = n % kStages;
+          unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
+          const int4 ra = *reinterpret_cast<const int4*>(rt + ti * 8), rb = *reinterpret_cast<const int4*>(rt + ti * 8 + 4);
+          mbar_wait(&mi.empty[s], ((n / kStages) & 1) ^ 1);
+          TC_TRACE(n, part ? EV_LOAD_V : EV_LOAD_ISSUE);
+          if (part == 0) mi.page_mask[s] = (vm32 >> (8 * ti)) & 0xFFu;
+          mbar_arrive_tx(&mi.full[s], (uint32_t)(kPartBytes + kTile * 4));
+          tma_gather4(st + part * kPartBytes, tm_c, ra.x, ra.y, ra.z, ra.w, &mi.full[s]);
+          tma_gather4(st + part * kPartBytes + 8192, tm_c, rb.x, rb.y, rb.z, rb.w, &mi.full[s]);
+          unsigned char* sdst = st + 2 * kPartBytes + part * kTile * 4;
+          if (ppt == 8) {
+            tma_gather4(sdst, tm_s, ra.x, ra.y, ra.z, ra.w, &mi.full[s]);
+            tma_gather4(sdst + 256, tm_s, rb.x, rb.y, rb.z, rb.w, &mi.full[s]);
+          } else {
+            const int4 pa = *reinterpret_cast<const int4*>(rt + 64 + ti * 8);
+            if (ppt == 4) {
+              tma_gather4(sdst, tm_s, pa.x, pa.y, pa.z, pa.w, &mi.full[s]);
+            } else {
+              bulk_g2s(sdst, scales + (int64_t)pa.x * bs, (uint32_t)(bs * 4), &mi.full[s]);
+              if (ppt == 2) bulk_g2s(sdst + bs * 4, scales + (int64_t)pa.y * bs, (uint32_t)(bs * 4), &mi.full[s]);
+            }
           }
-#pragma unroll
-          for (int l = 0; l < 4; ++l) dig[l][w4] = pk[l];
         }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          s01 += __shfl_xor_sync(0xFFFFFFFFu, s01, o);
-          s23 += __shfl_xor_sync(0xFFFFFFFFu, s23, o);
-        }
-        unsigned char* qop = sm + kOffQop + qb * kQopBytes;
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          const int row = hh * 4 + l;
-          *reinterpret_cast<uint4*>(qop + row * 128 + ((c ^ (row & 7)) << 4)) = make_uint4(dig[l][0], dig[l][1], dig[l][2], dig[l][3]);
-        }
-        if (c == 0) {
-          mi.qscale[qb][hh] = used ? ldexpf(a.sm_scale * 1.4426950408889634f, ex - 27) : 0.0f;
-          mi.qc01[qb][hh] = 8 * s01;
-          mi.qc23[qb][hh] = 8 * s23;
-        }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&mi.qready[qb]);
-        ++j;
       }
-      c = nx;
+      n = __shfl_sync(0xFFFFFFFFu, n, 0);
+      sg = nx;
       blk = blk_next;
+      ++segno;
     }
   } else if (warp == 1 || warp == 3) {
     // =============================================================== MMA issuers (one thread each): role 1 = QK^T, role 3 = PV
@@ -420,8 +376,8 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       const uint64_t qdesc0 = smem_desc(sptr(sm + kOffQop), 16, 1024, 2), wdesc0 = smem_desc(sptr(sm + kOffW), 128, 256, 0);
       if (warp == 1) {
         for (; c.valid; advance(c)) {
-          const int s = c.n % kStages, b = c.n & 1, qb = c.j & 1;
-          if (c.t == 0) mbar_wait(&mi.qready[qb], (c.j >> 1) & 1);
+          const int s = c.n % kStages, b = c.n & 1, qb = c.j % kQBufs;
+          if (c.t == 0) mbar_wait(&mi.qready[qb], (c.j / kQBufs) & 1);
           mbar_wait(&mi.sfree[b], ((c.n >> 1) & 1) ^ 1);          // S(n-2) has been read out of this TMEM buffer
           TC_TRACE(c.n, EV_S_WAITK);
           mbar_wait(&mi.kdec[s], (c.n / kStages) & 1);
@@ -460,6 +416,94 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
     const int r = w * 32 + lane;
     const uint32_t tlane = (uint32_t)(w * 32) << 16;
     const bool tracer = wi == 0 && lane == 0;
+    // A wait that is likely to block: ONE warp of the group polls the mbarrier (each probe costs issue slots: the hinted
+    // try_wait wakes every few dozen cycles), the other three sleep in a hardware named barrier, which costs nothing.
+    auto group_wait = [&](uint64_t* bar, uint32_t parity) {
+#if ECCQ_TC_GROUPWAIT
+      if ((wi & 3) == 0) mbar_wait(bar, parity);
+      named_bar_sync(2 + g, 128);
+#else
+      mbar_wait(bar, parity);
+#endif
+    };
+    // ---- query digits.  Warp wi < 4 prepares q-head wi of a pass: lane = 4 consecutive dims; the digits go to the item's
+    // buffer (three buffers: item i+2 is prepared when item i is finished, so the S issuer never waits for it and the
+    // buffer's previous user, item i-1, is long done).  It used to run on a producer warp, where its ~1000 instructions
+    // stalled the K loads for ~10 000 cycles at every item boundary.
+    int qitem = blockIdx.x, qj = 0;        // next item to prepare (candidate), its index among the non-empty items
+    auto prep_next_q = [&]() {
+      Item qi;
+      while (qitem < nitems && !get_item(a, qitem, qi)) qitem += gridDim.x;
+      if (qitem >= nitems) return;
+      if (wi < 4) {
+        const int qb = qj % kQBufs;
+        const int g0q = qi.pass * kHeadsPerPass;
+        const bool used = g0q + wi < G;
+        const int64_t qbase = ((int64_t)qi.seq * a.Hq + (int64_t)qi.kvh * G + g0q + wi) * kD + lane * 4;
+        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (used) {
+          if (a.q_dtype == ECCQ_F32) {
+            const float4 x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.q) + qbase);
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+          } else {
+            const uint2 x = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(a.q) + qbase);
+            if (a.q_dtype == ECCQ_F16) {
+              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&x.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&x.y));
+              v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+            } else {
+              v[0] = __uint_as_float(x.x << 16); v[1] = __uint_as_float(x.x & 0xFFFF0000u);
+              v[2] = __uint_as_float(x.y << 16); v[3] = __uint_as_float(x.y & 0xFFFF0000u);
+            }
+          }
+        }
+        float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+        // amax = m * 2^ex with m in [0.5, 1): |q| * 2^(27-ex) < 2^27
+        int ex = 0;
+        if (amax > 0.0f && amax < INFINITY) (void)frexpf(amax, &ex);
+        const float up = ldexpf(1.0f, 27 - ex);
+        uint32_t pk[4] = {0, 0, 0, 0};   // four dims of digit 0..3 (balanced base-128 digits, most significant first)
+        int32_t s01 = 0, s23 = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int32_t x = __float2int_rn(v[e] * up);
+          const int32_t d3 = ((x + 64) & 127) - 64; x = (x - d3) >> 7;
+          const int32_t d2 = ((x + 64) & 127) - 64; x = (x - d2) >> 7;
+          const int32_t d1 = ((x + 64) & 127) - 64; x = (x - d1) >> 7;
+          const int32_t d0 = x;
+          s01 += d0 * 128 + d1;
+          s23 += d2 * 128 + d3;
+          pk[0] |= (uint32_t)(d0 & 0xFF) << (8 * e);
+          pk[1] |= (uint32_t)(d1 & 0xFF) << (8 * e);
+          pk[2] |= (uint32_t)(d2 & 0xFF) << (8 * e);
+          pk[3] |= (uint32_t)(d3 & 0xFF) << (8 * e);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s01 += __shfl_xor_sync(0xFFFFFFFFu, s01, o);
+          s23 += __shfl_xor_sync(0xFFFFFFFFu, s23, o);
+        }
+        unsigned char* qop = sm + kOffQop + qb * kQopBytes;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int row = wi * 4 + l;        // B operand row = head * 4 + digit; K-major, 128-byte swizzle
+          *reinterpret_cast<uint32_t*>(qop + row * 128 + (((lane >> 2) ^ (row & 7)) << 4) + (lane & 3) * 4) = pk[l];
+        }
+        if (lane == 0) {
+          mi.qscale[qb][wi] = used ? ldexpf(a.sm_scale * 1.4426950408889634f, ex - 27) : 0.0f;
+          mi.qc01[qb][wi] = 8 * s01;
+          mi.qc23[qb][wi] = 8 * s23;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mi.qready[qb]);
+      }
+      qitem += gridDim.x;
+      ++qj;
+    };
+    prep_next_q();
+    prep_next_q();
     int n = 0, j = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       Item it;
@@ -477,8 +521,8 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
         }
         continue;
       }
-      const int qb = j & 1;
-      mbar_wait(&mi.qready[qb], (j >> 1) & 1);
+      const int qb = j % kQBufs;
+      mbar_wait(&mi.qready[qb], (j / kQBufs) & 1);
       float qs[2]; int32_t c01[2], c23[2];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) { qs[hh] = mi.qscale[qb][2 * g + hh]; c01[hh] = mi.qc01[qb][2 * g + hh]; c23[hh] = mi.qc23[qb][2 * g + hh]; }
@@ -503,7 +547,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       int o_waited = n - 1;                // last tile whose PV completion (oready phase) has been consumed
       auto wait_o = [&](int nn) {          // every oready phase is consumed exactly once, in order
         if (o_waited < nn) {
-          mbar_wait(&mi.oready[nn & 1], (nn >> 1) & 1);
+          group_wait(&mi.oready[nn & 1], (nn >> 1) & 1);
           if (tracer) TC_TRACE(nn, EV_O_READY);
           o_waited = nn;
         }
@@ -531,7 +575,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
         const bool valid = tok < it.c1 && ((mi.page_mask[s] >> (r >> lgbs)) & 1u);
         const float ks = reinterpret_cast<const float*>(st + 2 * kPartBytes)[r];
         const float vs = valid ? reinterpret_cast<const float*>(st + 2 * kPartBytes + kTile * 4)[r] : 0.0f;
-        mbar_wait(&mi.sready[b], (n >> 1) & 1);
+        group_wait(&mi.sready[b], (n >> 1) & 1);
         if (tracer) TC_TRACE(n, EV_SM_START);
         tc_after();
         uint32_t sr[8];
@@ -628,8 +672,8 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
           if (r == 0) { wsrow[kD] = (m_run[hh] <= kNegBig) ? -INFINITY : m_run[hh] * 0.6931471805599453f; wsrow[kD + 1] = L[hh]; }
         }
       }
-      named_bar_sync(1, kSoftmaxThreads);          // mi.fin is reused by the next item
-      mbar_arrive(&mi.qfree[qb]);
+      named_bar_sync(1, kSoftmaxThreads);          // mi.fin is reused by the next item; every S of this item has been consumed
+      prep_next_q();                               // item j + 2 into the buffer item j - 1 used
       ++j;
     }
   } else if (warp >= kFrontWarps) {

@@ -72,6 +72,7 @@ for _ in range(20):
 ms = statistics.median(ts)
 cwb = 4 * ((D + 2) // 3) / D if codec == "golay" else 1.0
 nbytes = Bq * ctx * (2 * HKV * D * cwb + 2 * HKV * 4)
-env = {k: v for k, v in os.environ.items() if k.startswith("ECCQ_")}
-print(f"attn {codec} interp={int(interp)} ctx={ctx} q={qdt} env={env}: {ms:.4f} ms (min {min(ts):.4f})  {nbytes / ms / 1e6:.0f} GB/s  "
-      f"{nbytes / ms / 1e6 / PEAK:.3f} of {PEAK:.0f}  max|err| vs fused-read route: {err}", flush=True)
+env = {k: v for k, v in os.environ.items() if k.startswith("ECCQ_") and k != "ECCQ_LIB"}
+lib_name = os.path.basename(os.environ.get("ECCQ_LIB", "main"))
+print(f"[{lib_name}] {ms:.4f} ms (min {min(ts):.4f})  {nbytes / ms / 1e6:.0f} GB/s  {nbytes / ms / 1e6 / PEAK:.3f} of {PEAK:.0f}   attn {codec} interp={int(interp)} "
+      f"ctx={ctx} q={qdt} env={env} max|err| vs fused-read route: {err}", flush=True)
