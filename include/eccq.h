@@ -139,6 +139,21 @@ int eccq_cache_correct_pages(const eccq_cache_desc* c, const int32_t* block_tabl
                              int nseq, int layer, int use_interpolation, uint8_t* k_pages, uint8_t* v_pages,
                              float* k_page_scales, float* v_page_scales, uint64_t* counters, void* stream);
 
+/* ---- unprotected comparison modes: paged scatter / gather of raw rows ----------------------------------------- */
+/* The "fp16" and "fp8" codecs of the shim (kv_cache/ecc_shim.py:511-570 write, :802-872 read): rows are stored as they are
+ * (fp16) or as float8_e4m3fn bytes (fp8), no scales.  k, v: [nseq, S, Hkv, row_bytes] raw bytes (row_bytes % 16 == 0);
+ * cache [num_blocks, L, Hkv, block_size * row_bytes].  inject = ECCQ_INJECT_PHILOX_REF flips bits of the low n_bits of
+ * every BYTE with the reference's per-(token, head) streams (N = row_bytes, seed_K = seed + inj_base + row, seed_V = +1;
+ * ecc_shim.py:547-556); other injectors are rejected. */
+int eccq_paged_rows_write(void* k_cache, void* v_cache, const void* k, const void* v, int row_bytes, int num_layers,
+                          int num_kv_heads, int block_size, const int32_t* block_table, int max_blocks,
+                          const int32_t* start_pos, int nseq, int S, int layer, int inject, int n_bits, float ber,
+                          int64_t seed, int64_t inj_base, uint64_t* counters, void* stream);
+/* gather the rows of whole contexts: k_out, v_out [nseq, out_stride_tokens, Hkv, row_bytes]; tokens past a context untouched */
+int eccq_paged_rows_read(const void* k_cache, const void* v_cache, void* k_out, void* v_out, int row_bytes, int num_layers,
+                         int num_kv_heads, int block_size, const int32_t* block_table, int max_blocks,
+                         const int32_t* context_lens, int nseq, int out_stride_tokens, int layer, void* stream);
+
 /* ---- ECC-fused paged decode attention ------------------------------------------------------------------- */
 /* paged_attention_ecc, kv_cache/attention_ecc.py:620-780 (kernel :264-426), generalised to GQA (kv_head = q_head/group,
  * SURVEY Q13), to hamming74/golay, to temporal interpolation, and split over the context (FlashDecoding).

@@ -66,6 +66,9 @@ _SIGNATURES = {
                                  c_float, c_int64, c_int64, _P, _P]),
     "eccq_cache_read": (c_int, [POINTER(CacheDesc), _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "eccq_cache_correct_pages": (c_int, [POINTER(CacheDesc), _P, c_int, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "eccq_paged_rows_write": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float,
+                                      c_int64, c_int64, _P, _P]),
+    "eccq_paged_rows_read": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int, c_int, _P]),
     "eccq_attention_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "eccq_paged_decode_attention": (c_int, [POINTER(CacheDesc), _P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_float,
                                             c_int, c_int, c_int, _P, c_int64, _P, _P]),

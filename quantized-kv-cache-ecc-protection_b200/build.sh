@@ -6,7 +6,7 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OBJ="$HERE/lib/obj"
 mkdir -p "$OBJ"
-UNITS="eccq_lib eccq_codecs eccq_cache_write eccq_cache_read eccq_attention eccq_attention_tc"
+UNITS="eccq_lib eccq_codecs eccq_cache_write eccq_cache_read eccq_paged_raw eccq_attention eccq_attention_tc"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
 pids=""
 for u in $UNITS; do

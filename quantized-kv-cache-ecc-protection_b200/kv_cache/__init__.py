@@ -6,8 +6,12 @@ from .attention_ecc import paged_attention_ecc, read_cache, reference_attention_
 from .ecc_shim import (ECCBackend, ECCDummyCache, ECCPagedAttentionShim, ECCShimConfig, SimpleBlockManager, _find_rotary_embedding,  # noqa: F401
                        _get_attention_params, compute_injection_seed, get_ecc_stats, patch_model_with_ecc_attention,
                        reset_ecc_cache)
+from .unprotected_shim import (UnprotectedBackend, UnprotectedDummyCache, UnprotectedPagedAttentionShim, UnprotectedShimConfig,  # noqa: F401
+                               get_unprotected_stats, patch_model_with_unprotected_attention, reset_unprotected_cache)
 
 __all__ = [
+    "UnprotectedShimConfig", "UnprotectedBackend", "UnprotectedPagedAttentionShim", "UnprotectedDummyCache",
+    "patch_model_with_unprotected_attention", "reset_unprotected_cache", "get_unprotected_stats",
     "ECCCacheConfig", "allocate_ecc_kv_cache", "get_physical_block", "create_block_table", "paged_attention_ecc",
     "reference_attention_ecc", "SimpleBlockManager", "ECCShimConfig", "ECCDummyCache", "ECCBackend", "ECCPagedAttentionShim",
     "patch_model_with_ecc_attention", "reset_ecc_cache", "get_ecc_stats", "_get_attention_params", "_find_rotary_embedding",

@@ -85,7 +85,8 @@ class ECCShimConfig:
     """
 
     SUPPORTED_CODECS = {"fp16", "fp8", "int4", "hamming74", "hamming84", "golay"}
-    CUDA_CODECS = ("int4", "hamming74", "hamming84", "golay")
+    CUDA_CODECS = ("fp16", "fp8", "int4", "hamming74", "hamming84", "golay")
+    RAW_CODECS = ("fp16", "fp8")      # unprotected comparison modes: rows stored unencoded, no scales (ecc_shim.py:240-247)
 
     def __init__(self, codec="hamming84", ber=0.0, block_size=16, num_blocks=256, inject_errors=False, seed=42,
                  use_interpolation=False, backend="cuda", injector="philox_ref", append=False):
@@ -107,18 +108,17 @@ class SimpleBlockManager:
 
     def __init__(self, num_blocks, block_size, num_layers, num_kv_heads, head_dim, device="cuda", codec="hamming84"):
         if codec not in ECCShimConfig.CUDA_CODECS:
-            raise NotImplementedError(
-                f"codec '{codec}' is an unprotected comparison mode of the reference (no ECC); the CUDA backend covers "
-                f"{ECCShimConfig.CUDA_CODECS} -- see DESIGN.md, out of scope")
+            raise ValueError(f"Unknown codec: {codec}")
         self.num_blocks, self.block_size, self.num_layers = num_blocks, block_size, num_layers
         self.num_kv_heads, self.head_dim, self.device, self.codec = num_kv_heads, head_dim, device, codec
         cw_per_token = (head_dim + 2) // 3 if codec == "golay" else head_dim
         self.values_per_head = self.codewords_per_head = block_size * cw_per_token
-        self.cache_dtype = torch.int32 if codec == "golay" else torch.uint8
-        self.needs_scales = True
+        self.cache_dtype = {"golay": torch.int32, "fp16": torch.float16, "fp8": torch.float8_e4m3fn}.get(codec, torch.uint8)
+        self.needs_scales = codec not in ECCShimConfig.RAW_CODECS
         shape = (num_blocks, num_layers, num_kv_heads, self.codewords_per_head)
         self.k_cache = torch.zeros(shape, dtype=self.cache_dtype, device=device)
         self.v_cache = torch.zeros(shape, dtype=self.cache_dtype, device=device)
+        # the reference allocates the scale arrays for every codec (ecc_shim.py:292-307); the raw codecs never touch them
         self.k_scales = torch.zeros(num_blocks, num_layers, num_kv_heads, block_size, dtype=torch.float32, device=device)
         self.v_scales = torch.zeros_like(self.k_scales)
         self._desc = None
@@ -219,6 +219,8 @@ class ECCBackend:
             v = v.to(k.dtype)
         k = k.reshape(B, S, H, D).contiguous()
         v = v.reshape(B, S, H, D).contiguous()
+        if cfg.codec in ECCShimConfig.RAW_CODECS:
+            return self._write_raw(k, v, layer_idx, seq_id)
         inject, km, vm = INJECT_NONE, None, None
         if self._flip_masks is not None:
             inject, (km, vm) = INJECT_MASK, self._flip_masks
@@ -252,6 +254,54 @@ class ECCBackend:
         if inject not in (INJECT_NONE, INJECT_MASK):
             self._injection_count += B * S * H  # one per (batch, pos, head), ecc_shim.py:643-651
 
+    def _rows_and_table(self, B, S, seq_id, layer_idx):
+        """Block table rows / start positions of a write: the reference's semantics (Q11: every batch row lands on positions
+        [0, S) of `seq_id`, the last one survives) or, with append=True, row b appended to sequence seq_id + b."""
+        m, cfg = self.manager, self.config
+        if cfg.append:
+            starts = [m.seq_layer_len.get((seq_id + b, layer_idx), 0) for b in range(B)]
+            for b in range(B):
+                m.allocate(seq_id + b, max(m.get_context_len(seq_id + b), starts[b] + S))
+                m.seq_layer_len[(seq_id + b, layer_idx)] = starts[b] + S
+            start = torch.tensor(starts, dtype=torch.int32).to(m.block_table.device, non_blocking=True)
+            return m.block_table[seq_id:seq_id + B], start, B, 0
+        if m.get_context_len(seq_id) < S:
+            m.allocate(seq_id, S)
+        return m.block_table[seq_id:seq_id + 1], None, 1, B - 1
+
+    def _write_raw(self, k, v, layer_idx, seq_id):
+        """Codecs "fp16" / "fp8" (ecc_shim.py:511-570): rows stored unencoded; fp8 rows take the reference's per-(token, head)
+        fault injection on their raw bytes (seed_K = seed + count, seed_V = +1, count += 1)."""
+        B, S, H, D = k.shape
+        m, cfg = self.manager, self.config
+        bt, start_dev, nseq, first = self._rows_and_table(B, S, seq_id, layer_idx)
+        inj_base = self._injection_count + first * S * H
+        k, v = k[first:], v[first:]
+        inject, n_bits = INJECT_NONE, 8
+        if cfg.codec == "fp16":
+            kr, vr = k.to(torch.float16).contiguous(), v.to(torch.float16).contiguous()
+        else:
+            kr, vr = k.to(torch.float8_e4m3fn).contiguous(), v.to(torch.float8_e4m3fn).contiguous()
+            if cfg.inject_errors and cfg.ber > 0:
+                inject = _lib.INJECT_PHILOX_REF
+        row_bytes = D * kr.element_size()
+        with device_of(kr):
+            check(load().eccq_paged_rows_write(ptr(m.k_cache), ptr(m.v_cache), ptr(kr), ptr(vr), row_bytes, m.num_layers, H, m.block_size,
+                                               ptr(bt), bt.shape[1], ptr(start_dev), nseq, S, int(layer_idx), inject, n_bits, float(cfg.ber),
+                                               int(cfg.seed), int(inj_base), ptr(self._counters), stream_of(kr)), "ECCBackend.write")
+        if inject != INJECT_NONE:
+            self._injection_count += B * S * H
+
+    def _read_raw(self, bt, cl, nseq, T, layer_idx):
+        m = self.manager
+        k = torch.zeros(nseq, T, m.num_kv_heads, m.head_dim, dtype=m.cache_dtype, device=m.k_cache.device)
+        v = torch.zeros_like(k)
+        with device_of(k):
+            check(load().eccq_paged_rows_read(ptr(m.k_cache), ptr(m.v_cache), ptr(k), ptr(v), m.head_dim * k.element_size(), m.num_layers,
+                                              m.num_kv_heads, m.block_size, ptr(bt), bt.shape[1], ptr(cl), nseq, T, int(layer_idx),
+                                              stream_of(k)), "ECCBackend.attend")
+        return k, v
+
     # -- attend ----------------------------------------------------------------------------------------------
     def attend(self, q, layer_idx, seq_id=0):
         B, Hq, Sq, D = q.shape
@@ -267,6 +317,12 @@ class ECCBackend:
             self._ctx_lens = (lens, torch.tensor(lens, dtype=torch.int32).to(q.device, non_blocking=True))
         cl = self._ctx_lens[1]
         bt = m.block_table[seq_id:seq_id + nseq]
+        if cfg.codec in ECCShimConfig.RAW_CODECS:
+            # ecc_shim.py:802-872: gather the rows, (fp8 -> fp16,) SDPA; no decode step, also for q_len == 1
+            k, v = self._read_raw(bt, cl, nseq, max(lens), layer_idx)
+            if cfg.codec == "fp8":
+                k, v = k.to(torch.float16), v.to(torch.float16)
+            return self._run_attention(q, k, v, self._append_mask(q, cl, lens, k.shape[1]))
         if Sq == 1:
             # fused paged decode attention for every codec (the reference: hamming84 without interpolation only)
             qd = q[:, :, 0, :]
@@ -285,15 +341,18 @@ class ECCBackend:
         dt = q.dtype if q.dtype in (torch.float32, torch.float16, torch.bfloat16) else torch.float32
         k, v = read_cache(m.k_cache, m.v_cache, m.k_scales, m.v_scales, bt, cl, layer_idx, m.block_size, D, cfg.codec,
                           use_interpolation=cfg.use_interpolation, out_dtype=dt, counters=self._counters, max_context=max(lens))
-        mask = None
-        if cfg.append and (min(lens) != max(lens) or lens[0] != Sq):
-            # chunked prefill / ragged batch: query t of row b sits at position lens[b]-Sq+t and sees keys <= that position
-            # (bottom-right aligned causal mask; it also hides the zero padding past a shorter sequence).  SDPA's
-            # is_causal is top-left aligned and is only right for a one-shot prefill of equal lengths.
-            key_pos = torch.arange(k.shape[1], device=q.device)
-            q_pos = cl.to(torch.int64)[:, None] - Sq + torch.arange(Sq, device=q.device)[None, :]
-            mask = (key_pos[None, None, :] <= q_pos[:, :, None])[:, None]          # [B, 1, Sq, ctx]
-        return self._run_attention(q, k, v, mask)
+        return self._run_attention(q, k, v, self._append_mask(q, cl, lens, k.shape[1]))
+
+    def _append_mask(self, q, cl, lens, ctx):
+        """Chunked prefill / ragged batch in append mode: query t of row b sits at position lens[b]-Sq+t and sees keys <= that
+        position (bottom-right aligned causal mask; it also hides the zero padding past a shorter sequence).  SDPA's
+        is_causal is top-left aligned and is only right for a one-shot prefill of equal lengths (the reference's only case)."""
+        Sq = q.shape[2]
+        if not self.config.append or (min(lens) == max(lens) and lens[0] == Sq):
+            return None
+        key_pos = torch.arange(ctx, device=q.device)
+        q_pos = cl.to(torch.int64)[:, None] - Sq + torch.arange(Sq, device=q.device)[None, :]
+        return (key_pos[None, None, :] <= q_pos[:, :, None])[:, None]                  # [B, 1, Sq, ctx]
 
     def _run_attention(self, q, k, v, attn_mask=None):
         """ecc_shim.py:1138-1164: GQA expand + SDPA, causal (top-left) when q_len > 1. k, v: [nseq, ctx, Hkv, D]."""

@@ -4,7 +4,7 @@ Generate the golden fixtures in this directory from the REFERENCE ITSELF.
 
 Run in the authoring container only (needs /root/reference, never the GPU box):
 
-    TRITON_INTERPRET=1 python tests/golden/make_golden.py [core] [gpt2]
+    TRITON_INTERPRET=1 python tests/golden/make_golden.py [core] [gpt2] [unprotected]
 
 The reference's @triton.jit kernels execute on CPU tensors under the Triton interpreter.  Its
 Python wrappers assert ``tensor.is_cuda``; we re-exec each wrapper's source with that one line
@@ -282,6 +282,49 @@ def gpt2_section(mods):
     np.savez_compressed(OUT / "gpt2_shim_vectors.npz", **out)
 
 
+def unprotected_section(mods):
+    """The unprotected comparison modes: ECCBackend with codec fp16 / fp8 / int4 (ecc_shim.py:511-625, :802-928) and
+    kv_cache/unprotected_shim.py's UnprotectedBackend (INT4, bit errors injected after the cache read), BER 0 and 0.05."""
+    shim = mods[6]
+    import kv_cache.unprotected_shim as un
+    import ecc_codecs.triton_kernels.fault_injection_triton as fi
+    un.inject_bit_errors_triton = fi.inject_bit_errors_triton          # the assert-stripped wrapper
+    T = torch.from_numpy
+    rng = np.random.default_rng(77)
+    B, S, Hq, Hkv, D, L, bs, nblk = 2, 21, 4, 2, 16, 2, 4, 12
+    kin = rng.standard_normal((B, S, Hkv * D)).astype(np.float32)
+    vin = rng.standard_normal((B, S, Hkv * D)).astype(np.float32)
+    qpre = rng.standard_normal((1, Hq, S, D)).astype(np.float32)
+    qdec = rng.standard_normal((1, Hq, 1, D)).astype(np.float32)
+    out = dict(k=kin, v=vin, q_prefill=qpre, q_decode=qdec, dims=np.array([B, S, Hq, Hkv, D, L, bs, nblk], dtype=np.int64))
+    for codec in ("fp16", "fp8", "int4"):
+        for ber in (0.0, 0.05):
+            tag = f"{codec}_ber{ber}"
+            cfg = shim.ECCShimConfig(codec=codec, ber=ber, block_size=bs, num_blocks=nblk, inject_errors=ber > 0, seed=42)
+            mgr = shim.SimpleBlockManager(nblk, bs, L, Hkv, D, device="cpu", codec=codec)
+            be = shim.ECCBackend(mgr, cfg, Hq)
+            be.write(T(kin), T(vin), layer_idx=1, seq_id=0)
+            raw = (lambda t: t.view(torch.uint8).numpy().copy()) if codec == "fp8" else (lambda t: t.numpy().copy())
+            out[tag + "_k_cache"], out[tag + "_v_cache"] = raw(mgr.k_cache), raw(mgr.v_cache)
+            out[tag + "_k_scales"], out[tag + "_v_scales"] = mgr.k_scales.numpy().copy(), mgr.v_scales.numpy().copy()
+            out[tag + "_out_prefill"] = be.attend(T(qpre), layer_idx=1, seq_id=0).numpy()
+            out[tag + "_out_decode"] = be.attend(T(qdec), layer_idx=1, seq_id=0).numpy()
+            out[tag + "_stats"] = np.array([be._injection_count, be._errors_corrected, be._errors_detected, be._total_values], dtype=np.int64)
+    for ber in (0.0, 0.05):
+        tag = f"unprotected_ber{ber}"
+        cfg = un.UnprotectedShimConfig(ber=ber, block_size=bs, num_blocks=nblk, inject_errors=ber > 0, seed=42)
+        mgr = shim.SimpleBlockManager(nblk, bs, L, Hkv, D, device="cpu", codec="int4")
+        be = un.UnprotectedBackend(mgr, cfg, Hq)
+        be.write(T(kin), T(vin), layer_idx=1, seq_id=0)
+        out[tag + "_k_cache"], out[tag + "_v_cache"] = mgr.k_cache.numpy().copy(), mgr.v_cache.numpy().copy()
+        out[tag + "_k_scales"], out[tag + "_v_scales"] = mgr.k_scales.numpy().copy(), mgr.v_scales.numpy().copy()
+        out[tag + "_out_prefill"] = be.attend(T(qpre), layer_idx=1, seq_id=0).numpy()
+        out[tag + "_out_prefill2"] = be.attend(T(qpre), layer_idx=1, seq_id=0).numpy()       # a second call: the next seed
+        out[tag + "_out_decode"] = be.attend(T(qdec), layer_idx=1, seq_id=0).numpy()
+        out[tag + "_stats"] = np.array([be._injection_count, be._bits_flipped, be._total_bits], dtype=np.int64)
+    np.savez_compressed(OUT / "unprotected_vectors.npz", **out)
+
+
 def main():
     sel = set(sys.argv[1:])
     mods = _strip_cuda_asserts()
@@ -289,6 +332,8 @@ def main():
         core_sections(mods)
     if not sel or "gpt2" in sel:
         gpt2_section(mods)
+    if not sel or "unprotected" in sel:
+        unprotected_section(mods)
     print("golden fixtures written to", OUT)
     for f in sorted(OUT.glob("*.npz")):
         print(f"  {f.name:28s} {f.stat().st_size:8d} B")

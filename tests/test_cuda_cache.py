@@ -194,8 +194,11 @@ def test_block_manager_and_stats_api():
         ECCShimConfig(codec="adaptive")
     with pytest.raises(ValueError):
         ECCShimConfig(backend="triton")
-    with pytest.raises(NotImplementedError):
-        SimpleBlockManager(8, 4, 2, 2, 16, device="cuda", codec="fp16")
+    raw = SimpleBlockManager(8, 4, 2, 2, 16, device="cuda", codec="fp16")          # unprotected comparison modes (ecc_shim.py:240-247)
+    assert raw.cache_dtype == torch.float16 and not raw.needs_scales and raw.k_cache.shape == (8, 2, 2, 4 * 16)
+    assert SimpleBlockManager(8, 4, 2, 2, 16, device="cuda", codec="fp8").cache_dtype == torch.float8_e4m3fn
+    with pytest.raises(ValueError):
+        SimpleBlockManager(8, 4, 2, 2, 16, device="cuda", codec="bogus")
 
 
 @pytest.mark.parametrize("codec", ["hamming84", "golay"])
