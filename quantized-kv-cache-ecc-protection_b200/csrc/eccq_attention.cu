@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
   const int pass = blockIdx.y - h * npass;
   const int i = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ctx = a.context_lens[i];
+  const int ctx = min(a.context_lens[i], a.max_blocks * g.bs);   // never walk past the block table
   const int c0 = split * a.chunk;
   const int c1 = min(ctx, c0 + a.chunk);
   const int g0 = pass * GP;                 // first q-head (within the group) of this pass

@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(LUT ? kLutWarps * 32 : kMmaThreads, LUT ? 1 : 
   unsigned char* smem = LUT ? upper : smem_all;   // merge area (and staging of the non-table variant)
   const uint32_t tab = kLutTableAddr;
   if (LUT) {
+    // the absolute-address layout assumes the dynamic window starts low enough for kLutLowWarps staging pairs below the table
+    if (base + kLutLowWarps * 2 * STAGE > kLutTableAddr) __trap();
     const uint8_t* one = reinterpret_cast<const uint8_t*>(pair_tab) + (CODEC == ECCQ_CODEC_H84 ? 256 : 0);   // hb(decode(c)), c = 0..255
     uint32_t* dst = reinterpret_cast<uint32_t*>(smem_all + (kLutTableAddr - base));
     for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) dst[(i >> 5) * 64 + (i & 31)] = (uint32_t)__ldg(one + (i >> 5)) << 8;
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(LUT ? kLutWarps * 32 : kMmaThreads, LUT ? 1 : 
   const int i = LUT ? item / (a.nsplit * ny) : (int)blockIdx.z;
   const int h = hy / npass;
   const int pass = hy - h * npass;
-  const int ctx = a.context_lens[i];
+  const int ctx = min(a.context_lens[i], a.max_blocks * g.bs);   // never walk past the block table
   const int c0 = split * a.chunk;
   const int c1 = min(ctx, c0 + a.chunk);
   const int g0 = pass * 8;
@@ -278,7 +280,8 @@ __global__ void __launch_bounds__(LUT ? kLutWarps * 32 : kMmaThreads, LUT ? 1 : 
       }
       // ---------------- P (x V scale) -> B fragments of PV
       const float vs0 = sVs[grow], vs1 = sVs[grow + 8];
-      const float pv[4] = {p[0] * vs0, p[1] * vs0, p[2] * vs1, p[3] * vs1};
+      // masked rows (past the context / unmapped page) contribute exactly 0 even when the caller's scale slot holds Inf / NaN
+      const float pv[4] = {t0ok ? p[0] * vs0 : 0.0f, t0ok ? p[1] * vs0 : 0.0f, t1ok ? p[2] * vs1 : 0.0f, t1ok ? p[3] * vs1 : 0.0f};
       const uint32_t ph0 = pack_half2(pv[0], pv[1]), ph1 = pack_half2(pv[2], pv[3]);
       const uint32_t pb0 = movmatrix_trans(ph0), pb1 = movmatrix_trans(ph1);
       uint32_t pl0 = 0, pl1 = 0;

@@ -26,10 +26,12 @@ _page_scratch: dict = {}
 
 def _corrected_pages(device, num_blocks, hkv, block_size, head_dim):
     """Scratch one-layer INT4 cache (pages + scales for K and V) for decode attention with interpolation."""
-    key = (device, num_blocks, hkv, block_size, head_dim)
+    # keyed by stream as well: two streams of one device must not share (and race on) one set of corrected pages
+    key = (device, torch.cuda.current_stream(device).cuda_stream, num_blocks, hkv, block_size, head_dim)
     t = _page_scratch.get(key)
     if t is None:
-        _page_scratch.clear()     # one geometry at a time: the scratch is as large as one layer of the cache
+        for k in [k for k in _page_scratch if k[:2] == key[:2]]:   # one geometry at a time per (device, stream): the scratch
+            del _page_scratch[k]                                    # is as large as one layer of the cache
         # zero-filled like the cache itself: slots past a ragged context are staged with their tile (and masked), so their
         # scales must be finite
         t = (torch.zeros(num_blocks, 1, hkv, block_size * head_dim, dtype=torch.uint8, device=device),
@@ -41,10 +43,13 @@ def _corrected_pages(device, num_blocks, hkv, block_size, head_dim):
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
-    ws = _workspaces.get(device)
+    # one workspace per (device, stream): concurrent callers on different streams never share split-KV partials, and a
+    # buffer that is outgrown is only ever replaced by its own stream (stream-ordered free in torch's caching allocator)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
+        _workspaces[key] = ws
     return ws
 
 
