@@ -24,6 +24,13 @@
 //   warps 8..   decode: LDS.128 raw codewords -> SWAR syndrome decode (eccq_common.cuh) -> STS.128 corrected nibbles IN PLACE
 //               at the 128-byte-swizzled position the UMMA descriptors expect
 // Partials (acc[D], m, l) per split go through the same workspace / attn_merge_kernel as the other attention kernels.
+//
+// Temporal interpolation of double-detected values (ECCShimConfig.use_interpolation, kv_cache/ecc_shim.py:1038-1059 +
+// interpolation_triton.py:120-159) runs in the SAME pass (template parameter INTERP): the decode warps leave bit 7 set on every
+// double-detected byte and raise a per-row flag; the MMA-issuer warp of the part (K: QK^T issuer, V: PV issuer) rewrites the
+// flagged rows -- (left + right + 1) >> 1 from the neighbouring token rows' pre-interpolation nibbles, SWAR on 16-byte chunks --
+// before it issues the tile's MMAs.  Neighbours across tiles: the previous tile's last row is kept in registers, the next
+// tile's first row is read after that tile's decode barrier; across splits: one 128-byte row from global memory per item.
 #include <cuda.h>   // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
 
 #include "eccq_attention.h"
@@ -67,6 +74,7 @@ struct Misc {
   alignas(16) float fin[kSoftmaxWarps][4];           // end-of-item reduction: l and sum(w) of the 2 heads per warp
   uint32_t page_mask[kStages];           // bit j: page j of the stage's tile was loaded
   alignas(16) int32_t rowtab[2][128];                // per producer: [2 segments][32] gather rows, then [2][32] pages (scale rows)
+  alignas(16) uint32_t rowflag[kStages][2][4];       // INTERP: bit r of [stage][part]: token row r of the tile holds a double-detected value
   uint32_t pv_fresh[2];                  // 1: PV of this weight buffer starts a new accumulation in TMEM (written before wready)
   uint32_t tmem_base;
 };
@@ -229,7 +237,18 @@ __device__ __forceinline__ uint32_t decode_nibbles(uint32_t w, FlagCount& fc, bo
   return w & M0F;
 }
 
-template <int CODEC, bool COUNT, int NDEC>
+// swizzled byte offset of 16-byte chunk c of token row r inside a K or V tile (128-byte swizzle, K-major / MN-major alike)
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 x;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(addr));
+  return x;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 x) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+}
+
+template <int CODEC, bool COUNT, int NDEC, bool INTERP>
 __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(const __grid_constant__ Args a, uint64_t* counters) {
   extern __shared__ __align__(16) unsigned char eccq_tc_smem[];
   const uint32_t raw = sptr(eccq_tc_smem);
@@ -257,6 +276,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       mbar_init(&mi.oready[b], 1);
     }
     for (int b = 0; b < kQBufs; ++b) mbar_init(&mi.qready[b], 4);   // one arrival per preparing warp (= per q-head of the pass)
+    for (int i = 0; i < kStages * 2 * 4; ++i) (&mi.rowflag[0][0][0])[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -353,6 +373,180 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       blk = blk_next;
       ++segno;
     }
+  } else if (INTERP && (warp == 1 || warp == 3)) {
+    // =============================================================== MMA issuers with temporal interpolation (whole warp)
+    // Same protocol as the plain issuers below; before a tile's MMAs go out the warp rewrites the token rows its part's decode
+    // warps flagged.  Lane = (row slot lane / 8 of the current group of four flagged rows, 16-byte chunk lane % 8).
+    const int part = warp == 1 ? 0 : 1;
+    const int c8 = lane & 7, grp = lane >> 3;
+    const unsigned char* cache = part ? a.g.v_cache : a.g.k_cache;
+    const int lh0 = a.layer * a.g.H, LH = a.g.L * a.g.H;
+    const uint32_t stage0 = sptr(sm + kOffStages) + (uint32_t)(part * kPartBytes);
+    struct Cur { int item, t, n, j; Item it; bool valid; };
+    auto seek = [&](Cur& c) {
+      while (c.item < nitems && !get_item(a, c.item, c.it)) c.item += gridDim.x;
+      c.valid = c.item < nitems;
+    };
+    auto advance = [&](Cur& c) {
+      ++c.n;
+      if (++c.t == c.it.ntiles) { c.t = 0; ++c.j; c.item += gridDim.x; seek(c); }
+    };
+    Cur c;
+    c.item = (int)blockIdx.x; c.t = 0; c.n = 0; c.j = 0; c.valid = false;
+    seek(c);
+    const uint64_t kdesc0 = smem_desc(sptr(sm + kOffStages), 16, 1024, 2), vdesc0 = smem_desc(sptr(sm + kOffStages + kPartBytes), 16, 1024, 2);
+    const uint64_t qdesc0 = smem_desc(sptr(sm + kOffQop), 16, 1024, 2), wdesc0 = smem_desc(sptr(sm + kOffW), 128, 256, 0);
+    uint32_t prev[4] = {0, 0, 0, 0}, hdn[4] = {0, 0, 0, 0};   // pre-interpolation nibbles: row before the tile, row after the item
+    bool prev_ok = false, hdn_ok = false;
+    uint4 hraw = make_uint4(0, 0, 0, 0);   // the two boundary rows as loaded (decoded after the tile's barriers: the round trip overlaps the waits)
+    bool hraw_ok = false;
+    for (; c.valid; advance(c)) {
+      const int s = c.n % kStages, b = c.n & 1;
+      const Item& it = c.it;
+      if (c.t == 0) {
+        // neighbours across the split boundaries: token c0 - 1 (row group 0) and token c1 (row group 1), straight from the cache
+        const int ctx = min(a.context_lens[it.seq], a.max_blocks * bs);
+        const int tokh = grp == 0 ? it.c0 - 1 : it.c1;
+        bool ok = grp < 2 && tokh >= 0 && tokh < ctx;
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (ok) {
+          const int blk = a.block_table[(int64_t)it.seq * a.max_blocks + (tokh >> lgbs)];
+          ok = blk >= 0;
+          if (ok) x = *reinterpret_cast<const uint4*>(cache + ((int64_t)(blk * LH + lh0 + it.kvh) * bs + (tokh & (bs - 1))) * kD + c8 * 16);
+        }
+        hraw = x;
+        hraw_ok = ok;
+      }
+      // the decoded tile first: it is ready long before the TMEM buffer (S) / the weights (PV) are, so the rewrite below runs
+      // while this warp would otherwise be waiting for those
+      mbar_wait(part ? &mi.vdec[s] : &mi.kdec[s], (c.n / kStages) & 1);
+      if (part == 0 && lane == 0) TC_TRACE(c.n, EV_S_WAITK);
+      if (c.t == 0) {
+        uint32_t y[4], fl;
+        hamming_decode4<ECCQ_CODEC_H84>(hraw.x, y[0], fl); hamming_decode4<ECCQ_CODEC_H84>(hraw.y, y[1], fl);
+        hamming_decode4<ECCQ_CODEC_H84>(hraw.z, y[2], fl); hamming_decode4<ECCQ_CODEC_H84>(hraw.w, y[3], fl);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { prev[k] = __shfl_sync(0xFFFFFFFFu, y[k], c8); hdn[k] = __shfl_sync(0xFFFFFFFFu, y[k], 8 + c8); }
+        prev_ok = __shfl_sync(0xFFFFFFFFu, (int)hraw_ok, 0) != 0;
+        hdn_ok = __shfl_sync(0xFFFFFFFFu, (int)hraw_ok, 8) != 0;
+      }
+      // ---- rewrite the flagged rows of this part of the tile
+      {
+        const uint32_t stp = stage0 + (uint32_t)(s * kStageBytes);
+        const int tokbase = (it.tile0 + c.t) * kTile;
+        const uint32_t pm = mi.page_mask[s];
+        auto row_ok = [&](int r) { return tokbase + r < it.c1 && ((pm >> (r >> lgbs)) & 1u) != 0; };
+        const uint4 fw = *reinterpret_cast<const uint4*>(&mi.rowflag[s][part][0]);
+        uint32_t m[4] = {fw.x, fw.y, fw.z, fw.w};
+        const uint4 lastrow = lds128(stp + swz(kTile - 1, c8));   // this tile's last row before any rewrite: the next tile's left neighbour
+        if (m[0] | m[1] | m[2] | m[3]) {
+          uint32_t nx[4] = {0, 0, 0, 0};
+          bool nx_ok = false;
+          if (m[3] >> 31) {   // the tile's last row needs the row after it
+            if (c.t + 1 < it.ntiles) {
+              const int sn = (c.n + 1) % kStages;
+              mbar_wait(part ? &mi.vdec[sn] : &mi.kdec[sn], ((c.n + 1) / kStages) & 1);
+              const uint4 x = lds128(stage0 + (uint32_t)(sn * kStageBytes) + swz(0, c8));
+              nx[0] = x.x & M0F; nx[1] = x.y & M0F; nx[2] = x.z & M0F; nx[3] = x.w & M0F;
+              nx_ok = tokbase + kTile < it.c1 && (mi.page_mask[sn] & 1u) != 0;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) nx[k] = hdn[k];
+              nx_ok = hdn_ok;
+            }
+          }
+          int last_r = -2;               // last row of the previous group (already rewritten in shared memory) ...
+          uint32_t last_pre[4] = {0, 0, 0, 0};   // ... and its pre-interpolation nibbles
+          while (m[0] | m[1] | m[2] | m[3]) {
+            int rs[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // the four lowest flagged rows, ascending
+              int r = -1;
+              if (m[0]) { r = __ffs(m[0]) - 1; m[0] &= m[0] - 1; }
+              else if (m[1]) { r = 32 + __ffs(m[1]) - 1; m[1] &= m[1] - 1; }
+              else if (m[2]) { r = 64 + __ffs(m[2]) - 1; m[2] &= m[2] - 1; }
+              else if (m[3]) { r = 96 + __ffs(m[3]) - 1; m[3] &= m[3] - 1; }
+              rs[k] = r;
+            }
+            const int r = grp == 0 ? rs[0] : grp == 1 ? rs[1] : grp == 2 ? rs[2] : rs[3];
+            uint4 self = make_uint4(0, 0, 0, 0);
+            uint32_t up[4] = {0, 0, 0, 0}, dn[4] = {0, 0, 0, 0};
+            bool upok = false, dnok = false;
+            if (r >= 0) {
+              self = lds128(stp + swz(r, c8));
+              if (r == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) up[k] = prev[k];
+                upok = prev_ok;
+              } else if (r - 1 == last_r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) up[k] = last_pre[k];
+                upok = row_ok(r - 1);
+              } else {
+                const uint4 x = lds128(stp + swz(r - 1, c8));
+                up[0] = x.x & M0F; up[1] = x.y & M0F; up[2] = x.z & M0F; up[3] = x.w & M0F;
+                upok = row_ok(r - 1);
+              }
+              if (r == kTile - 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dn[k] = nx[k];
+                dnok = nx_ok;
+              } else {
+                const uint4 x = lds128(stp + swz(r + 1, c8));
+                dn[0] = x.x & M0F; dn[1] = x.y & M0F; dn[2] = x.z & M0F; dn[3] = x.w & M0F;
+                dnok = row_ok(r + 1);
+              }
+            }
+            __syncwarp();   // every read of this group precedes its writes: neighbours are pre-interpolation values (no cascade)
+            const uint32_t sw[4] = {self.x, self.y, self.z, self.w};
+            uint32_t nw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t sn4 = sw[k] & M0F;
+              const uint32_t l4 = upok ? up[k] : sn4, r4 = dnok ? dn[k] : sn4;   // a missing neighbour is replaced by the value itself
+              nw[k] = interp4(sn4, l4, r4, (sw[k] >> 7) & M01);
+            }
+            last_r = rs[3];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) last_pre[k] = __shfl_sync(0xFFFFFFFFu, sw[k] & M0F, 24 + c8);
+            if (r >= 0) sts128(stp + swz(r, c8), make_uint4(nw[0], nw[1], nw[2], nw[3]));
+            __syncwarp();
+          }
+          if (lane < 4) mi.rowflag[s][part][lane] = 0;
+          fence_async_smem();
+        }
+        prev[0] = lastrow.x & M0F; prev[1] = lastrow.y & M0F; prev[2] = lastrow.z & M0F; prev[3] = lastrow.w & M0F;
+        prev_ok = row_ok(kTile - 1);
+      }
+      if (part == 0) {
+        if (c.t == 0) mbar_wait(&mi.qready[(c.j % kQBufs)], (c.j / kQBufs) & 1);
+        mbar_wait(&mi.sfree[b], ((c.n >> 1) & 1) ^ 1);          // S(n-2) has been read out of this TMEM buffer
+      } else {
+        mbar_wait(&mi.wready[b], (c.n >> 1) & 1);               // W(n) and its fresh flag are in shared memory
+      }
+      __syncwarp();
+      if (lane == 0) {
+        TC_TRACE(c.n, part ? EV_PV_ISSUE : EV_S_ISSUE);
+        tc_after();
+        if (part == 0) {
+          const int qb = c.j % kQBufs;
+          const uint64_t ka = kdesc0 + (uint64_t)(s * (kStageBytes >> 4)), qa = qdesc0 + (uint64_t)(qb * (kQopBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_i8(tmem + b * 16, ka + 2 * k, qa + 2 * k, kIdescS, k > 0);
+          tc_commit(&mi.sready[b]);
+        } else {
+          const uint32_t keep = mi.pv_fresh[b] ? 0u : 1u;
+          const uint64_t va = vdesc0 + (uint64_t)(s * (kStageBytes >> 4)), wa = wdesc0 + (uint64_t)(b * (kWBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_i8(tmem + 32, va + 256 * k, wa + 32 * k, kIdescO, k > 0 ? 1u : keep);
+          tc_commit(&mi.oready[b]);
+          tc_commit(&mi.empty[s]);
+        }
+      }
+      __syncwarp();
+    }
+    if (part == 1 && lane == 0)
+      for (int back = min(c.n, kStages); back > 0; --back) mbar_wait(&mi.empty[(c.n - back) % kStages], ((c.n - back) / kStages) & 1);
   } else if (warp == 1 || warp == 3) {
     // =============================================================== MMA issuers (one thread each): role 1 = QK^T, role 3 = PV
     // Two independent issue streams: S(n) goes out as soon as the K half of tile n is decoded and its TMEM buffer has been
@@ -722,10 +916,32 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
               const int row = (dw + i * NDEC) * 4 + (lane >> 3);
               cnt = do_count && tokbase + row < it.c1 && ((pm >> (row >> lgbs)) & 1u);
             }
-            const uint32_t y0 = decode_nibbles<CODEC, COUNT>(x[part][i].x, fc, cnt);
-            const uint32_t y1 = decode_nibbles<CODEC, COUNT>(x[part][i].y, fc, cnt);
-            const uint32_t y2 = decode_nibbles<CODEC, COUNT>(x[part][i].z, fc, cnt);
-            const uint32_t y3 = decode_nibbles<CODEC, COUNT>(x[part][i].w, fc, cnt);
+            uint32_t y0, y1, y2, y3;
+            if constexpr (INTERP) {
+              // double-detected bytes keep bit 7 set (flag byte 0xFF: only doubles have bit 0) and raise their row's flag; the
+              // issuer warp of the part rewrites those rows before the MMAs read them
+              const uint32_t w4[4] = {x[part][i].x, x[part][i].y, x[part][i].z, x[part][i].w};
+              uint32_t y4[4], any = 0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint32_t fl;
+                hamming_decode4<ECCQ_CODEC_H84>(w4[k], y4[k], fl);
+                if (COUNT) fc.add(cnt ? fl : 0u);
+                const uint32_t mk = (fl << 7) & 0x80808080u;
+                y4[k] |= mk;
+                any |= mk;
+              }
+              if (any) {
+                const int row = (dw + i * NDEC) * 4 + (lane >> 3);
+                atomicOr(&mi.rowflag[s][part][row >> 5], 1u << (row & 31));
+              }
+              y0 = y4[0]; y1 = y4[1]; y2 = y4[2]; y3 = y4[3];
+            } else {
+              y0 = decode_nibbles<CODEC, COUNT>(x[part][i].x, fc, cnt);
+              y1 = decode_nibbles<CODEC, COUNT>(x[part][i].y, fc, cnt);
+              y2 = decode_nibbles<CODEC, COUNT>(x[part][i].z, fc, cnt);
+              y3 = decode_nibbles<CODEC, COUNT>(x[part][i].w, fc, cnt);
+            }
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(st + part * kPartBytes + wr_off[i]), "r"(y0), "r"(y1), "r"(y2), "r"(y3) : "memory");
           }
           fence_async_smem();
@@ -740,6 +956,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       if (lane == 0 && counters != nullptr) {
         if (ns) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + ECCQ_CTR_CORRECTED, (unsigned long long)ns);
         if (nd) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + ECCQ_CTR_DETECTED, (unsigned long long)nd);
+        if (INTERP && nd) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + ECCQ_CTR_INTERPOLATED, (unsigned long long)nd);
       }
     }
   }
@@ -784,9 +1001,9 @@ static bool tensor_map_rows(CUtensorMap& out, const void* base, uint64_t rows, u
   return true;
 }
 
-template <int CODEC, bool COUNT, int NDEC>
+template <int CODEC, bool COUNT, int NDEC, bool INTERP = false>
 static int launch(const Args& a, uint64_t* counters, cudaStream_t st) {
-  auto kern = attn_tc_kernel<CODEC, COUNT, NDEC>;
+  auto kern = attn_tc_kernel<CODEC, COUNT, NDEC, INTERP>;
   const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);   // per device
   if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
   const int nitems = a.nseq * a.g.H * a.npass * a.nsplit;
@@ -806,7 +1023,7 @@ extern "C" int eccq_tc_trace_read(long long* out_host) {
 // outside it, < 0 on error.  May lower a.nsplit / raise a.chunk (fewer, longer splits; the workspace was sized for more).
 int try_attn_tc(const CacheGeom& g, AttnArgs& a, int q_dtype, uint64_t* counters, cudaStream_t st) {
   static const int env = [] { const char* v = std::getenv("ECCQ_ATTN_TC"); return v && *v ? std::atoi(v) : 1; }();
-  if (!env || g.codec == ECCQ_CODEC_GOLAY || a.interp || g.D != tc::kD) return 0;
+  if (!env || g.codec == ECCQ_CODEC_GOLAY || (a.interp && g.codec != ECCQ_CODEC_H84) || g.D != tc::kD) return 0;
   if (g.bs < 16 || g.bs > tc::kTile || (tc::kTile % g.bs) != 0) return 0;
   if (!aligned16(g.k_cache) || !aligned16(g.v_cache) || !aligned16(g.k_scales) || !aligned16(g.v_scales)) return 0;
   const int G = a.Hq / g.H;
@@ -834,7 +1051,9 @@ int try_attn_tc(const CacheGeom& g, AttnArgs& a, int q_dtype, uint64_t* counters
   int rc;
 #define ECCQ_TC_CASE(C, CNT)                                            \
   rc = ndec == 8 ? tc::launch<C, CNT, 8>(t, counters, st) : tc::launch<C, CNT, 16>(t, counters, st)
-  if (a.count_errors) {
+  if (a.interp) {
+    rc = a.count_errors ? tc::launch<ECCQ_CODEC_H84, true, 16, true>(t, counters, st) : tc::launch<ECCQ_CODEC_H84, false, 16, true>(t, counters, st);
+  } else if (a.count_errors) {
     switch (g.codec) {
       case ECCQ_CODEC_H84: ECCQ_TC_CASE(ECCQ_CODEC_H84, true); break;
       case ECCQ_CODEC_H74: ECCQ_TC_CASE(ECCQ_CODEC_H74, true); break;

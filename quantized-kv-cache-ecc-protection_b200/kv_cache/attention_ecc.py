@@ -12,6 +12,7 @@ Differences from the reference, all deliberate and tested:
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -92,7 +93,11 @@ def paged_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_sc
         lib = load()
         nbytes = lib.eccq_attention_workspace_bytes(B, Hq, D, max_blocks * block_size)
         ws = _workspace(qd.device, nbytes)
-        if interp or codec == "golay":
+        # Hamming(8,4) + interpolation at head_dim 128: ONE pass -- the tcgen05 kernel rewrites double-detected values from
+        # their temporal neighbours inside the tile pipeline (csrc/eccq_attention_tc.cu, INTERP variant).
+        single_pass = interp and D == 128 and block_size in (16, 32, 64, 128) and os.environ.get("ECCQ_ATTN_TC", "1") != "0" \
+            and os.environ.get("ECCQ_ATTN_INTERP_TWO_PASS", "0") == "0"
+        if (interp and not single_pass) or codec == "golay":
             # temporal neighbours span pages (and Golay codewords span values): resolve them once with the streaming read
             # kernels into corrected INT4 pages (same paged layout, one layer), then attend over those with the INT4 tile
             # path.  Falls through to the general kernel for geometries the streaming kernels do not cover.

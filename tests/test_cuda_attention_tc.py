@@ -132,6 +132,93 @@ def test_unmapped_blocks_inside_the_context(oracle):
     assert (int(ctr[0]), int(ctr[1])) == (corr, det)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs", [16, 32, 64, 128])
+@pytest.mark.parametrize("ber", [0.02, 0.08])
+def test_single_pass_interpolation(oracle, bs, ber):
+    """Hamming(8,4) + temporal interpolation inside the tile pipeline (INTERP variant) against the oracle: double errors in
+    adjacent rows (no cascade), in the first / last row of a tile (neighbour in the previous / next tile), at the first and the
+    last token of a context (clamped neighbour), ragged last tiles, counters incl. `interpolated`.  BER 0.08 flags nearly
+    every row of every tile (2 % of the values are double errors)."""
+    from eccq_b200.kv_cache import paged_attention_ecc
+    Hq, Hkv, D = 8, 2, 128
+    lens = [700, 129, 128, 1, 0, 257, 2]
+    oc, bt = build_cache(oracle, "hamming84", Hkv, D, bs, lens, seed=3 * bs + int(100 * ber), ber=ber)
+    q = np.random.default_rng(1).standard_normal((len(lens), Hq, D)).astype(np.float32)
+    ref, corr, det = oracle.paged_decode_attention(q, oc, bt, np.array(lens), 1, use_interpolation=True)
+    ref0, _, _ = oracle.paged_decode_attention(q, oc, bt, np.array(lens), 1, use_interpolation=False)
+    assert np.abs(ref - ref0).max() > 1e-3       # interpolation matters on this input
+    ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+    out = paged_attention_ecc(dev(q), dev(oc.k_cache), dev(oc.v_cache), dev(bt), dev(np.array(lens, np.int32)), dev(oc.k_scales), 1, bs,
+                              codec="hamming84", v_scales=dev(oc.v_scales), use_interpolation=True, counters=ctr)
+    assert np.abs(out.cpu().numpy() - ref).max() < TOL_F32
+    assert (int(ctr[0]), int(ctr[1]), int(ctr[5])) == (corr, det, det)
+    out2 = paged_attention_ecc(dev(q), dev(oc.k_cache), dev(oc.v_cache), dev(bt), dev(np.array(lens, np.int32)), dev(oc.k_scales), 1, bs,
+                               codec="hamming84", v_scales=dev(oc.v_scales), use_interpolation=True)      # variant without counters
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.gpu
+def test_single_pass_interpolation_across_splits(oracle):
+    """Contexts longer than one 2 048-token split: the neighbour of a split's first / last row lives in another work item
+    (fetched from the cache by the issuer warps); several items per CTA; GQA group 8 = two passes over the same tiles."""
+    from eccq_b200.kv_cache import paged_attention_ecc
+    D, bs = 128, 16
+    lens = [6200, 4096, 2049]
+    for Hq, Hkv in ((8, 2), (8, 1)):
+        oc, bt = build_cache(oracle, "hamming84", Hkv, D, bs, lens, seed=Hq + Hkv, ber=0.03)
+        # double errors exactly at the split boundaries of sequence 0 (tokens 2047 | 2048 and 4095 | 4096), every dim of head 0
+        for tok in (2047, 2048, 4095, 4096):
+            blk, slot = bt[0, tok // bs], tok % bs
+            oc.k_cache[blk, 1, 0, slot * D:(slot + 1) * D] ^= 0x11
+            oc.v_cache[blk, 1, 0, slot * D:(slot + 1) * D] ^= 0x06
+        q = np.random.default_rng(2).standard_normal((len(lens), Hq, D)).astype(np.float32)
+        ref, corr, det = oracle.paged_decode_attention(q, oc, bt, np.array(lens), 1, use_interpolation=True, precision=np.float64)
+        ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+        out = paged_attention_ecc(dev(q), dev(oc.k_cache), dev(oc.v_cache), dev(bt), dev(np.array(lens, np.int32)), dev(oc.k_scales), 1, bs,
+                                  v_scales=dev(oc.v_scales), use_interpolation=True, counters=ctr)
+        assert np.abs(out.cpu().numpy() - ref).max() < TOL_F32
+        assert (int(ctr[0]), int(ctr[1]), int(ctr[5])) == (corr, det, det)
+
+
+@pytest.mark.gpu
+def test_single_pass_interpolation_matches_two_pass_route():
+    """The single-pass kernel against the round-1 route (streaming read into corrected INT4 pages, then the tile kernel) at the
+    C5 geometry with 4 096-token contexts: same corrected nibbles -> outputs agree to fp32 rounding, counters identical."""
+    code = r"""
+import os, sys, torch
+sys.path.insert(0, %r)
+from eccq_b200 import _lib
+from eccq_b200.kv_cache import SimpleBlockManager, paged_attention_ecc
+two_pass = os.environ.get("ECCQ_ATTN_INTERP_TWO_PASS") == "1"
+torch.manual_seed(0)
+B, ctx, Hq, Hkv, D, bs = 4, 4096, 32, 8, 128, 16
+m = SimpleBlockManager(B * ctx // bs, bs, 1, Hkv, D, device="cuda", codec="hamming84")
+m.block_table = torch.randperm(B * ctx // bs, generator=torch.Generator().manual_seed(3)).to(torch.int32).view(B, ctx // bs).cuda()
+lib, P = _lib.load(), _lib.ptr
+sp = _lib.c_void_p(torch.cuda.current_stream().cuda_stream)
+kk = torch.randn(B, ctx, Hkv * D, device="cuda", dtype=torch.float16)
+_lib.check(lib.eccq_cache_write(m.desc(), P(kk), P(kk.flip(1)), _lib.ECCQ_F16, P(m.block_table), ctx // bs, None, B, ctx, 0,
+                                _lib.INJECT_PHILOX_FAST, None, None, 2e-2, 7, 0, None, sp), "cache_write")
+q = torch.randn(B, Hq, D, device="cuda")
+cl = torch.tensor([4096, 4000, 2100, 77], dtype=torch.int32, device="cuda")
+ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+out = paged_attention_ecc(q, m.k_cache, m.v_cache, m.block_table, cl, m.k_scales, 0, bs, v_scales=m.v_scales, use_interpolation=True, counters=ctr)
+torch.save((out.cpu(), ctr.cpu()), sys.argv[1])
+""" % str(ROOT)
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for two_pass in ("0", "1"):
+            path = os.path.join(tmp, f"o{two_pass}.pt")
+            env = dict(os.environ, ECCQ_ATTN_INTERP_TWO_PASS=two_pass)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+            outs.append(torch.load(path))
+    (o1, c1), (o2, c2) = outs
+    assert (o1 - o2).abs().max() < 2e-5
+    assert c1.tolist() == c2.tolist() and c1[1] > 1000
+
+
 _CHILD = r"""
 import sys
 sys.path.insert(0, {root!r})

@@ -2,6 +2,7 @@
 """Pipeline trace of the tcgen05 decode-attention kernel (library built with -DECCQ_TC_TRACE, selected with ECCQ_LIB):
 runs one C5-shard call and prints, for CTA 0, the SM clock of every hand-off per tile relative to the tile's load issue."""
 import ctypes
+import os
 import sys
 from pathlib import Path
 
@@ -21,14 +22,17 @@ nblk_seq = ctx // BS
 nblk = Bq * nblk_seq
 m = SimpleBlockManager(nblk, BS, 1, HKV, D, device=dev, codec="hamming84")
 m.block_table = torch.randperm(nblk, generator=torch.Generator().manual_seed(3)).to(torch.int32).view(Bq, nblk_seq).to(dev)
-m.k_cache.random_(0, 256)
-m.v_cache.random_(0, 256)
-m.k_scales.fill_(0.1)
-m.v_scales.fill_(0.1)
+INTERP = os.environ.get("TC_TRACE_INTERP", "0") == "1"
+sp = _lib.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+for s0 in range(0, ctx, 4096):   # valid codewords with flips at BER 1e-3, as in bench.py / attn_bench.py
+    kk = torch.randn(Bq, 4096, HKV * D, device=dev, dtype=torch.float16)
+    start = torch.full((Bq,), s0, dtype=torch.int32, device=dev)
+    _lib.check(lib.eccq_cache_write(m.desc(), P(kk), P(kk.flip(1)), _lib.ECCQ_F16, P(m.block_table), nblk_seq, P(start), Bq, 4096, 0,
+                                    _lib.INJECT_PHILOX_FAST, None, None, 1e-3, 1, s0, None, sp), "cache_write")
 q = torch.randn(Bq, HQ, D, device=dev, dtype=torch.float16)
 cl = torch.full((Bq,), ctx, dtype=torch.int32, device=dev)
 for _ in range(3):
-    paged_attention_ecc(q, m.k_cache, m.v_cache, m.block_table, cl, m.k_scales, 0, BS, v_scales=m.v_scales)
+    paged_attention_ecc(q, m.k_cache, m.v_cache, m.block_table, cl, m.k_scales, 0, BS, v_scales=m.v_scales, use_interpolation=INTERP)
 torch.cuda.synchronize()
 raw = ctypes.CDLL(str(_lib.LIB_PATH))
 buf = np.zeros(512 * 16, dtype=np.int64)
