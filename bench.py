@@ -561,7 +561,35 @@ def bench_attention(torch, dev, lib, _lib, paged_attention_ecc, SimpleBlockManag
     ms = e0.elapsed_time(e1) / n
     nbytes = Bq * ctx * (2 * HKV * D + 2 * HKV * 4)
     peak, _ = hbm_peak()
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(reps):
+            fn()
+        t1.record()
+        torch.cuda.synchronize(dev)
+        return t0.elapsed_time(t1) / reps
+
+    # the same shard with temporal interpolation of double-detected values: ONE pass (INTERP variant of the tcgen05 kernel) and
+    # the round-1 route (streaming read into corrected INT4 pages, then the tile kernel) selected by the environment
+    variants = {}
+    try:
+        ms_i = timed(lambda: paged_attention_ecc(q, m.k_cache, m.v_cache, m.block_table, cl, m.k_scales, 0, BS, v_scales=m.v_scales,
+                                                 use_interpolation=True))
+        variants["hamming84_interp_single_pass"] = {"ms": ms_i, "roofline_frac": nbytes / (ms_i * 1e-3) / 1e9 / peak, "vs_plain": ms_i / ms}
+        os.environ["ECCQ_ATTN_INTERP_TWO_PASS"] = "1"
+        ms_2 = timed(lambda: paged_attention_ecc(q, m.k_cache, m.v_cache, m.block_table, cl, m.k_scales, 0, BS, v_scales=m.v_scales,
+                                                 use_interpolation=True))
+        variants["hamming84_interp_two_pass"] = {"ms": ms_2, "roofline_frac": nbytes / (ms_2 * 1e-3) / 1e9 / peak}
+    except Exception as exc:
+        variants["error"] = repr(exc)
+    finally:
+        os.environ.pop("ECCQ_ATTN_INTERP_TWO_PASS", None)
     return {"workload": "C5 shard: batch 8 x 32768 ctx, Hq 32, Hkv 8, D 128, block 16, Hamming(8,4), q_len 1, one layer",
+            "cache_fill_ber": 1e-3, "variants": variants,
             "ms_per_layer_call": ms, "context_tokens_per_s_per_gpu": Bq * ctx / (ms * 1e-3),
             "context_tokens_per_s_all_gpus": world * Bq * ctx / (ms * 1e-3),
             "generated_tokens_per_s_32_layers": world * Bq / (32 * ms * 1e-3), "gbs": nbytes / (ms * 1e-3) / 1e9,

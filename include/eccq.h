@@ -165,6 +165,19 @@ int eccq_paged_decode_attention(const eccq_cache_desc* c, const void* q, void* o
                                 int use_interpolation, int v_use_k_scales, int count_errors, void* workspace,
                                 int64_t workspace_bytes, uint64_t* counters, void* stream);
 
+/* ---- ECC-fused causal prefill attention (q_len > 1) ------------------------------------------------------ */
+/* Replaces the read half of ECCBackend.attend for q_len > 1 -- gather pages, decode, interpolate, dequantise to fp32 K/V
+ * [ctx, Hkv, D], repeat_interleave, SDPA(is_causal) -- kv_cache/ecc_shim.py:739-1089 and _run_attention :1138-1164, with ONE
+ * kernel that consumes the codewords directly (ECC decode in the K/V prologue, no K/V materialisation, no library kernel).
+ * q, out: [batch, Hq, Sq, D] q_dtype.  nseq == batch: batch row b attends over sequence b; nseq == 1: every batch row
+ * attends over the one shared context (the reference's write semantics).  Query t sits at position
+ * context_len - Sq + t and sees the tokens at or before it (equal to SDPA's top-left is_causal mask when context_len == Sq,
+ * the reference's only case; chunked prefill in append mode otherwise).  Rows with no visible token -> zeros.
+ * count_errors != 0 accumulates CORRECTED / DETECTED once per decoded codeword of the context (as the reference's decode does). */
+int eccq_paged_prefill_attention(const eccq_cache_desc* c, const void* q, void* out, int q_dtype, const int32_t* block_table,
+                                 int max_blocks, const int32_t* context_lens, int nseq, int batch, int Hq, int Sq, int layer,
+                                 float sm_scale, int use_interpolation, int count_errors, uint64_t* counters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

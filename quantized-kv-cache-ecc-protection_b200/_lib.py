@@ -72,6 +72,8 @@ _SIGNATURES = {
     "eccq_attention_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "eccq_paged_decode_attention": (c_int, [POINTER(CacheDesc), _P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_float,
                                             c_int, c_int, c_int, _P, c_int64, _P, _P]),
+    "eccq_paged_prefill_attention": (c_int, [POINTER(CacheDesc), _P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_float,
+                                             c_int, c_int, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

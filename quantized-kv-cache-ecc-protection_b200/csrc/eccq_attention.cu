@@ -27,7 +27,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // EPL = values per lane. Hamming/int4: EPL = 4*NCH (one 32-bit word of codeword bytes per 128-value chunk);
 // Golay: EPL = 3*NIT (one codeword per 32-codeword sweep).
-template <typename TQ, int CODEC, int GP, int NCH>
+// PREFILL = true turns the same kernel into the ECC-fused causal prefill attention (replaces the gather + decode + fp32
+// materialisation + repeat_interleave + SDPA of ECCBackend.attend, kv_cache/ecc_shim.py:1067-1089, :1138-1164): the GP
+// "heads" of a CTA become GP consecutive query positions of ONE q-head, every token row is decoded once per CTA in the K/V
+// prologue exactly as for decode attention (interpolation included), a causal mask is applied per query, and the CTA writes
+// the normalised output itself (no context split, no merge kernel).  grid = (query blocks, Hq, batch rows).
+template <typename TQ, int CODEC, int GP, int NCH, bool PREFILL = false>
 __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g, AttnArgs a, uint64_t* counters) {
   constexpr bool GOLAY = CODEC == ECCQ_CODEC_GOLAY;
   constexpr int VPC = GOLAY ? 3 : 4;   // values per lane per chunk
@@ -45,18 +50,21 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
   }
   float* s_red = reinterpret_cast<float*>(p);  // [kAttnWarps][GP][EPL*32 + 2]
 
-  const int split = blockIdx.x;
+  const int split = PREFILL ? 0 : blockIdx.x;
   const int G = a.Hq / g.H;
   const int npass = (G + GP - 1) / GP;
-  const int h = blockIdx.y / npass;
-  const int pass = blockIdx.y - h * npass;
-  const int i = blockIdx.z;
+  const int h = PREFILL ? (int)blockIdx.y / G : (int)blockIdx.y / npass;
+  const int pass = PREFILL ? 0 : blockIdx.y - h * npass;
+  const int i = PREFILL ? (a.nseq == 1 ? 0 : (int)blockIdx.z) : (int)blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ctx = min(a.context_lens[i], a.max_blocks * g.bs);   // never walk past the block table
-  const int c0 = split * a.chunk;
-  const int c1 = min(ctx, c0 + a.chunk);
-  const int g0 = pass * GP;                 // first q-head (within the group) of this pass
-  const int ng = min(GP, G - g0);
+  // prefill: queries t0 .. t0+ng-1 of q-head blockIdx.y, batch row blockIdx.z; query t sits at position qstart + t
+  const int t0 = PREFILL ? (int)blockIdx.x * GP : 0;
+  const int qstart = ctx - a.Sq;
+  const int c0 = PREFILL ? 0 : split * a.chunk;
+  const int g0 = PREFILL ? 0 : pass * GP;   // first q-head (within the group) of this pass
+  const int ng = PREFILL ? min(GP, a.Sq - t0) : min(GP, G - g0);
+  const int c1 = PREFILL ? max(0, min(ctx, qstart + t0 + ng)) : min(ctx, c0 + a.chunk);   // prefill: tokens the block's last query sees
   const int32_t* bt = a.block_table + (int64_t)i * a.max_blocks;
   const int rowbytes = GOLAY ? g.cw * 4 : g.D;
   const int64_t page_bytes = (int64_t)g.bs * rowbytes;
@@ -76,7 +84,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
 #pragma unroll
       for (int v = 0; v < VPC; ++v) {
         const int e = elem(ch, v);
-        qreg[gi][ch * VPC + v] = (gi < ng && e >= 0) ? ldq<TQ>(a.q, ((int64_t)i * a.Hq + (int64_t)h * G + g0 + gi) * g.D + e) * a.sm_scale : 0.0f;
+        const int64_t qrow = PREFILL ? ((int64_t)blockIdx.z * a.Hq + blockIdx.y) * a.Sq + t0 + gi : (int64_t)i * a.Hq + (int64_t)h * G + g0 + gi;
+        qreg[gi][ch * VPC + v] = (gi < ng && e >= 0) ? ldq<TQ>(a.q, qrow * g.D + e) * a.sm_scale : 0.0f;
       }
   if (GOLAY) __syncthreads();
 
@@ -88,15 +97,39 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
     for (int x = 0; x < EPL; ++x) acc[gi][x] = 0.0f;
   }
   uint32_t ncorr = 0, ndet = 0;
-  const bool do_count = a.count_errors && pass == 0;
+  // prefill: the last query block of the first q-head of a group (first batch row of a shared context) sees every token once
+  const bool do_count = PREFILL ? a.count_errors && (int)blockIdx.x == (int)gridDim.x - 1 && (int)blockIdx.y % G == 0 && (a.nseq > 1 || blockIdx.z == 0)
+                                : a.count_errors && pass == 0;
 
-  // decode the values this lane owns of token `tok` from `cache`; returns false if the token has no block
-  auto decode_row = [&](const uint8_t* cache, int tok, float (&val)[EPL], uint32_t (&dbl)[NCH], bool count, int& blk_out, int& slot_out) -> bool {
+  // The codeword words this lane owns of a token's K and V rows + its scales, loaded one loop iteration ahead of their use: the
+  // block-table entry, the row and the scales are three dependent global loads, and a warp walks its tokens serially, so
+  // without the prefetch every token pays that round trip (short prefill launches are bound by exactly this chain).
+  struct Raw { uint32_t k[NCH], v[NCH]; float ksc, vsc; int blk; };
+  auto load_raw = [&](int tok) -> Raw {
+    Raw r;
     const int lb = tok / g.bs, slot = tok - lb * g.bs;
-    const int blk = bt[lb];
-    blk_out = blk; slot_out = slot;
-    if (blk < 0) return false;
-    const uint8_t* row = cache + page_index(g, blk, a.layer, h) * page_bytes + (int64_t)slot * rowbytes;
+    r.blk = bt[lb];
+    r.ksc = r.vsc = 0.0f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) r.k[ch] = r.v[ch] = 0u;
+    if (r.blk < 0) return r;
+    const int64_t pg = page_index(g, r.blk, a.layer, h);
+    const int64_t off = pg * page_bytes + (int64_t)slot * rowbytes;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int w = GOLAY ? ch * 32 + lane : ch * 32 + lane;           // word index inside the row
+      const bool in = GOLAY ? w < g.cw : w * 4 < g.D;
+      if (in) {
+        r.k[ch] = __ldg(reinterpret_cast<const uint32_t*>(g.k_cache + off) + w);
+        r.v[ch] = __ldg(reinterpret_cast<const uint32_t*>(g.v_cache + off) + w);
+      }
+    }
+    r.ksc = __ldg(g.k_scales + pg * g.bs + slot);
+    r.vsc = a.v_use_k_scales ? r.ksc : __ldg(g.v_scales + pg * g.bs + slot);
+    return r;
+  };
+  // decode the values this lane owns of a row from its loaded words
+  auto decode_row = [&](const uint32_t (&raw)[NCH], float (&val)[EPL], uint32_t (&dbl)[NCH], bool count) {
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       dbl[ch] = 0;
@@ -105,7 +138,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
         uint32_t d = 0;
         if (j < g.cw) {
           uint32_t cnt;
-          d = golay_decode1(s_lo, s_hi, s_syn, __ldg(reinterpret_cast<const uint32_t*>(row) + j), cnt);
+          d = golay_decode1(s_lo, s_hi, s_syn, raw[ch], cnt);
           if (count) { if (cnt == 4u) ++ndet; else ncorr += cnt; }
         }
         val[ch * 3] = (float)(int)(d & 0xF) - 8.0f;
@@ -115,7 +148,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
         const int e0 = ch * 128 + lane * 4;
         uint32_t nib = 0x08080808u;
         if (e0 < g.D) {
-          const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(row + e0));
+          const uint32_t w = raw[ch];
           if (CODEC == ECCQ_CODEC_H84) {
             const Dec4 d = h84_decode4(w);
             nib = d.nib; dbl[ch] = h84_double4(d);
@@ -132,7 +165,6 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
         val[ch * 4] = __uint_as_float(nib);
       }
     }
-    return true;
   };
   // Hamming: nibble word of a neighbour token for chunk ch (pre-interpolation decode)
   auto neighbour_word = [&](const uint8_t* cache, int tok, int ch) -> uint32_t {
@@ -159,15 +191,17 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
     }
   };
 
+  Raw nxt;
+  if (c0 + warp < c1) nxt = load_raw(c0 + warp);
   for (int tok = c0 + warp; tok < c1; tok += kAttnWarps) {
+    const Raw cur = nxt;
+    if (tok + kAttnWarps < c1) nxt = load_raw(tok + kAttnWarps);
+    if (cur.blk < 0) continue;          // unmapped block: its tokens take no part (the reference's gather skips it)
     float kv[EPL];
     uint32_t dbl[NCH];
-    int blk, slot;
-    if (!decode_row(g.k_cache, tok, kv, dbl, do_count, blk, slot)) continue;
+    decode_row(cur.k, kv, dbl, do_count);
     finish_row(g.k_cache, tok, kv, dbl);
-    const int64_t sidx = page_index(g, blk, a.layer, h) * g.bs + slot;
-    const float ksc = __ldg(g.k_scales + sidx);
-    const float vsc = a.v_use_k_scales ? ksc : __ldg(g.v_scales + sidx);
+    const float ksc = cur.ksc, vsc = cur.vsc;
     float s[GP];
 #pragma unroll
     for (int gi = 0; gi < GP; ++gi) {
@@ -177,10 +211,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
       s[gi] = warp_sum(d) * ksc;
     }
     float vv[EPL];
-    decode_row(g.v_cache, tok, vv, dbl, do_count, blk, slot);
+    decode_row(cur.v, vv, dbl, do_count);
     finish_row(g.v_cache, tok, vv, dbl);
 #pragma unroll
     for (int gi = 0; gi < GP; ++gi) {
+      if (PREFILL && tok > qstart + t0 + gi) continue;   // causal mask (warp-uniform)
       const float mn = fmaxf(m[gi], s[gi]);
       const float alpha = __expf(m[gi] - mn);   // exp(-inf) = 0 on the first token
       const float pw = __expf(s[gi] - mn);
@@ -216,6 +251,18 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
 #pragma unroll
       for (int x = 0; x < EPL; ++x) o[x] += src[x * 32 + lane] * f;
     }
+    if constexpr (PREFILL) {
+      TQ* orow = reinterpret_cast<TQ*>(a.out) + (((int64_t)blockIdx.z * a.Hq + blockIdx.y) * a.Sq + t0 + gi) * g.D;
+      const float inv = Lsum > 0.0f ? 1.0f / Lsum : 0.0f;      // no visible token (empty context): zeros
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int v = 0; v < VPC; ++v) {
+          const int e = elem(ch, v);
+          if (e >= 0) orow[e] = Cvt<TQ>::to(o[ch * VPC + v] * inv);
+        }
+      continue;
+    }
     const int qh = h * G + g0 + gi;
     float* wsrow = a.ws + (((int64_t)i * a.Hq + qh) * a.nsplit + split) * (g.D + 2);
 #pragma unroll
@@ -228,9 +275,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(CacheGeom g,
     if (lane == 0) { wsrow[g.D] = M; wsrow[g.D + 1] = Lsum; }
   }
   if (a.count_errors) {
-    const int idx[2] = {ECCQ_CTR_CORRECTED, ECCQ_CTR_DETECTED};
-    const uint32_t val[2] = {ncorr, ndet};
-    block_accumulate<2>(counters, idx, val);
+    const int idx[3] = {ECCQ_CTR_CORRECTED, ECCQ_CTR_DETECTED, ECCQ_CTR_INTERPOLATED};
+    const uint32_t val[3] = {ncorr, ndet, a.interp ? ndet : 0u};   // every double-detected value is interpolated (ecc_shim.py:1038-1059)
+    block_accumulate<3>(counters, idx, val);
   }
 }
 
@@ -331,6 +378,39 @@ static int run_attn(const CacheGeom& g, const AttnArgs& a_in, uint64_t* counters
   return ECCQ_OK;
 }
 
+// ---- prefill (q_len > 1): the PREFILL instantiation of attn_partial_kernel, GP = queries per CTA
+template <typename TQ, int CODEC, int GP, int NCH>
+static int launch_prefill(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  constexpr int VPC = CODEC == ECCQ_CODEC_GOLAY ? 3 : 4;
+  const size_t smem = (CODEC == ECCQ_CODEC_GOLAY ? 4096 * 4 + 256 : 0) + sizeof(float) * kAttnWarps * GP * (VPC * NCH * 32 + 2);
+  auto kern = attn_partial_kernel<TQ, CODEC, GP, NCH, true>;
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
+  }
+  dim3 grid((a.Sq + GP - 1) / GP, a.Hq, a.qbatch);
+  kern<<<grid, kAttnThreads, smem, st>>>(g, a, counters);
+  return ECCQ_OK;
+}
+template <typename TQ, int CODEC>
+static int dispatch_prefill(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  const int per_chunk = CODEC == ECCQ_CODEC_GOLAY ? 96 : 128;
+  const int nch = (g.D + per_chunk - 1) / per_chunk;
+  if (nch > (CODEC == ECCQ_CODEC_GOLAY ? 3 : 2)) return fail(ECCQ_EUNSUPPORTED, "paged_prefill_attention: head_dim too large (max 256)");
+  if (nch == 1) return launch_prefill<TQ, CODEC, 8, 1>(g, a, counters, st);
+  if (nch == 2) return launch_prefill<TQ, CODEC, 4, 2>(g, a, counters, st);
+  return launch_prefill<TQ, CODEC, 4, (CODEC == ECCQ_CODEC_GOLAY ? 3 : 2)>(g, a, counters, st);
+}
+template <typename TQ>
+static int run_prefill(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  switch (g.codec) {
+    case ECCQ_CODEC_H74: return dispatch_prefill<TQ, ECCQ_CODEC_H74>(g, a, counters, st);
+    case ECCQ_CODEC_H84: return dispatch_prefill<TQ, ECCQ_CODEC_H84>(g, a, counters, st);
+    case ECCQ_CODEC_GOLAY: return dispatch_prefill<TQ, ECCQ_CODEC_GOLAY>(g, a, counters, st);
+    default: return dispatch_prefill<TQ, ECCQ_CODEC_INT4>(g, a, counters, st);
+  }
+}
+
 }  // namespace eccq
 
 #include "eccq_attention_mma.cuh"
@@ -378,4 +458,37 @@ extern "C" int eccq_paged_decode_attention(const eccq_cache_desc* c, const void*
   }
   if (rc) return rc;
   return check_launch("paged_decode_attention");
+}
+
+extern "C" int eccq_paged_prefill_attention(const eccq_cache_desc* c, const void* q, void* out, int q_dtype,
+                                            const int32_t* block_table, int max_blocks, const int32_t* context_lens, int nseq,
+                                            int batch, int Hq, int Sq, int layer, float sm_scale, int use_interpolation,
+                                            int count_errors, uint64_t* counters, void* stream) {
+  CacheGeom g;
+  if (!make_geom(c, g)) return fail(ECCQ_EINVAL, "paged_prefill_attention: bad cache descriptor");
+  if (nseq < 0 || batch < 0 || Hq <= 0 || Hq % g.H != 0 || Sq <= 0 || layer < 0 || layer >= g.L || max_blocks <= 0 || !block_table || !context_lens)
+    return fail(ECCQ_EINVAL, "paged_prefill_attention: bad arguments");
+  if (nseq != 1 && nseq != batch) return fail(ECCQ_EINVAL, "paged_prefill_attention: nseq must be 1 (shared context) or equal to batch");
+  if (nseq == 0 || batch == 0) return ECCQ_OK;
+  if (!q || !out) return fail(ECCQ_EINVAL, "paged_prefill_attention: null pointer");
+  if (batch > 65535 || Hq > 65535) return fail(ECCQ_EUNSUPPORTED, "paged_prefill_attention: batch / head count above the grid limits");
+  if (g.codec != ECCQ_CODEC_GOLAY && (g.D % 4 != 0 || (reinterpret_cast<uintptr_t>(g.k_cache) & 3) || (reinterpret_cast<uintptr_t>(g.v_cache) & 3)))
+    return fail(ECCQ_EUNSUPPORTED, "paged_prefill_attention: head_dim must be a multiple of 4 for byte codecs");
+  if (int rc = ensure_tables()) return rc;
+  AttnArgs a;
+  a.q = q; a.out = out; a.block_table = block_table; a.context_lens = context_lens; a.ws = nullptr;
+  a.max_blocks = max_blocks; a.nseq = nseq; a.Hq = Hq; a.layer = layer; a.sm_scale = sm_scale;
+  a.nsplit = 1; a.chunk = max_blocks * g.bs; a.force_general = 1;
+  a.interp = use_interpolation && g.codec == ECCQ_CODEC_H84; a.v_use_k_scales = 0; a.count_errors = count_errors && counters;
+  a.Sq = Sq; a.qbatch = batch;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  switch (q_dtype) {
+    case ECCQ_F32: rc = run_prefill<float>(g, a, counters, st); break;
+    case ECCQ_F16: rc = run_prefill<__half>(g, a, counters, st); break;
+    case ECCQ_BF16: rc = run_prefill<__nv_bfloat16>(g, a, counters, st); break;
+    default: return fail(ECCQ_EINVAL, "paged_prefill_attention: bad dtype");
+  }
+  if (rc) return rc;
+  return check_launch("paged_prefill_attention");
 }

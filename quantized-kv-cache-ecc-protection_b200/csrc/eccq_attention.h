@@ -14,6 +14,9 @@ struct AttnArgs {
   int max_blocks, nseq, Hq, layer, nsplit, chunk;
   float sm_scale;
   int interp, v_use_k_scales, count_errors, force_general;
+  // prefill (q_len > 1, causal; eccq_paged_prefill_attention): q / out are [qbatch, Hq, Sq, D]; query t of batch row b sits at
+  // position ctx_b - Sq + t; nseq == 1 with qbatch > 1 = one shared context (the reference's batch semantics)
+  int Sq = 1, qbatch = 0;
 };
 
 // eccq_attention_tc.cu: 1 = the tcgen05 kernel took the launch (partials written, the caller merges), 0 = geometry outside it,

@@ -27,10 +27,12 @@
 //
 // Temporal interpolation of double-detected values (ECCShimConfig.use_interpolation, kv_cache/ecc_shim.py:1038-1059 +
 // interpolation_triton.py:120-159) runs in the SAME pass (template parameter INTERP): the decode warps leave bit 7 set on every
-// double-detected byte and raise a per-row flag; the MMA-issuer warp of the part (K: QK^T issuer, V: PV issuer) rewrites the
-// flagged rows -- (left + right + 1) >> 1 from the neighbouring token rows' pre-interpolation nibbles, SWAR on 16-byte chunks --
-// before it issues the tile's MMAs.  Neighbours across tiles: the previous tile's last row is kept in registers, the next
-// tile's first row is read after that tile's decode barrier; across splits: one 128-byte row from global memory per item.
+// double-detected byte and set bit (row) of their 16-byte column chunk's bitmap.  Interpolation runs along the token axis at a
+// fixed dim, so the eight column chunks of a part are independent: once every row of the part is stored (the part's decode
+// barrier), decode warp w < 8 rewrites the flagged cells of K chunk w, warp 8 + w those of V chunk w -- (left + right + 1) >> 1
+// from the neighbouring rows' pre-interpolation nibbles, SWAR on 16 bytes, all reads of a 32-row group before its writes (no
+// cascade) -- and arrives on the barrier the MMA issuer of the part waits for.  A neighbour outside the tile (row -1 / 128: the
+// previous / next tile or split) is fetched from the cache in global memory and decoded on the spot (rare: one cell in ~300).
 #include <cuda.h>   // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
 
 #include "eccq_attention.h"
@@ -66,6 +68,7 @@ constexpr int kOffW = kOffQop + kQBufs * kQopBytes;
 constexpr int kOffMisc = kOffW + 2 * kWBytes;
 struct Misc {
   uint64_t full[kStages], kdec[kStages], vdec[kStages], empty[kStages];
+  uint64_t kfix[kStages], vfix[kStages];   // INTERP: the part's flagged cells are rewritten (one arrival per column-chunk worker warp)
   uint64_t sready[2], sfree[2], wready[2], oready[2], qready[kQBufs];
   float qscale[kQBufs][kHeadsPerPass];        // 2^(e-27) * sm_scale * log2(e) per head (0 for unused heads)
   int32_t qc01[kQBufs][kHeadsPerPass];        // 8 * sum_d (d0*128 + d1)
@@ -74,7 +77,7 @@ struct Misc {
   alignas(16) float fin[kSoftmaxWarps][4];           // end-of-item reduction: l and sum(w) of the 2 heads per warp
   uint32_t page_mask[kStages];           // bit j: page j of the stage's tile was loaded
   alignas(16) int32_t rowtab[2][128];                // per producer: [2 segments][32] gather rows, then [2][32] pages (scale rows)
-  alignas(16) uint32_t rowflag[kStages][2][4];       // INTERP: bit r of [stage][part]: token row r of the tile holds a double-detected value
+  alignas(16) uint32_t colflag[kStages][2][8][4];    // INTERP: [stage][part][16-byte column chunk]: bit r = token row r holds a double-detected value
   uint32_t pv_fresh[2];                  // 1: PV of this weight buffer starts a new accumulation in TMEM (written before wready)
   uint32_t tmem_base;
 };
@@ -268,6 +271,8 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       mbar_init(&mi.kdec[s], NDEC);
       mbar_init(&mi.vdec[s], NDEC);
       mbar_init(&mi.empty[s], 1);
+      mbar_init(&mi.kfix[s], 8);
+      mbar_init(&mi.vfix[s], 8);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&mi.sready[b], 1);
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       mbar_init(&mi.oready[b], 1);
     }
     for (int b = 0; b < kQBufs; ++b) mbar_init(&mi.qready[b], 4);   // one arrival per preparing warp (= per q-head of the pass)
-    for (int i = 0; i < kStages * 2 * 4; ++i) (&mi.rowflag[0][0][0])[i] = 0;
+    for (int i = 0; i < kStages * 2 * 8 * 4; ++i) (&mi.colflag[0][0][0][0])[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -373,180 +378,6 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       blk = blk_next;
       ++segno;
     }
-  } else if (INTERP && (warp == 1 || warp == 3)) {
-    // =============================================================== MMA issuers with temporal interpolation (whole warp)
-    // Same protocol as the plain issuers below; before a tile's MMAs go out the warp rewrites the token rows its part's decode
-    // warps flagged.  Lane = (row slot lane / 8 of the current group of four flagged rows, 16-byte chunk lane % 8).
-    const int part = warp == 1 ? 0 : 1;
-    const int c8 = lane & 7, grp = lane >> 3;
-    const unsigned char* cache = part ? a.g.v_cache : a.g.k_cache;
-    const int lh0 = a.layer * a.g.H, LH = a.g.L * a.g.H;
-    const uint32_t stage0 = sptr(sm + kOffStages) + (uint32_t)(part * kPartBytes);
-    struct Cur { int item, t, n, j; Item it; bool valid; };
-    auto seek = [&](Cur& c) {
-      while (c.item < nitems && !get_item(a, c.item, c.it)) c.item += gridDim.x;
-      c.valid = c.item < nitems;
-    };
-    auto advance = [&](Cur& c) {
-      ++c.n;
-      if (++c.t == c.it.ntiles) { c.t = 0; ++c.j; c.item += gridDim.x; seek(c); }
-    };
-    Cur c;
-    c.item = (int)blockIdx.x; c.t = 0; c.n = 0; c.j = 0; c.valid = false;
-    seek(c);
-    const uint64_t kdesc0 = smem_desc(sptr(sm + kOffStages), 16, 1024, 2), vdesc0 = smem_desc(sptr(sm + kOffStages + kPartBytes), 16, 1024, 2);
-    const uint64_t qdesc0 = smem_desc(sptr(sm + kOffQop), 16, 1024, 2), wdesc0 = smem_desc(sptr(sm + kOffW), 128, 256, 0);
-    uint32_t prev[4] = {0, 0, 0, 0}, hdn[4] = {0, 0, 0, 0};   // pre-interpolation nibbles: row before the tile, row after the item
-    bool prev_ok = false, hdn_ok = false;
-    uint4 hraw = make_uint4(0, 0, 0, 0);   // the two boundary rows as loaded (decoded after the tile's barriers: the round trip overlaps the waits)
-    bool hraw_ok = false;
-    for (; c.valid; advance(c)) {
-      const int s = c.n % kStages, b = c.n & 1;
-      const Item& it = c.it;
-      if (c.t == 0) {
-        // neighbours across the split boundaries: token c0 - 1 (row group 0) and token c1 (row group 1), straight from the cache
-        const int ctx = min(a.context_lens[it.seq], a.max_blocks * bs);
-        const int tokh = grp == 0 ? it.c0 - 1 : it.c1;
-        bool ok = grp < 2 && tokh >= 0 && tokh < ctx;
-        uint4 x = make_uint4(0, 0, 0, 0);
-        if (ok) {
-          const int blk = a.block_table[(int64_t)it.seq * a.max_blocks + (tokh >> lgbs)];
-          ok = blk >= 0;
-          if (ok) x = *reinterpret_cast<const uint4*>(cache + ((int64_t)(blk * LH + lh0 + it.kvh) * bs + (tokh & (bs - 1))) * kD + c8 * 16);
-        }
-        hraw = x;
-        hraw_ok = ok;
-      }
-      // the decoded tile first: it is ready long before the TMEM buffer (S) / the weights (PV) are, so the rewrite below runs
-      // while this warp would otherwise be waiting for those
-      mbar_wait(part ? &mi.vdec[s] : &mi.kdec[s], (c.n / kStages) & 1);
-      if (part == 0 && lane == 0) TC_TRACE(c.n, EV_S_WAITK);
-      if (c.t == 0) {
-        uint32_t y[4], fl;
-        hamming_decode4<ECCQ_CODEC_H84>(hraw.x, y[0], fl); hamming_decode4<ECCQ_CODEC_H84>(hraw.y, y[1], fl);
-        hamming_decode4<ECCQ_CODEC_H84>(hraw.z, y[2], fl); hamming_decode4<ECCQ_CODEC_H84>(hraw.w, y[3], fl);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { prev[k] = __shfl_sync(0xFFFFFFFFu, y[k], c8); hdn[k] = __shfl_sync(0xFFFFFFFFu, y[k], 8 + c8); }
-        prev_ok = __shfl_sync(0xFFFFFFFFu, (int)hraw_ok, 0) != 0;
-        hdn_ok = __shfl_sync(0xFFFFFFFFu, (int)hraw_ok, 8) != 0;
-      }
-      // ---- rewrite the flagged rows of this part of the tile
-      {
-        const uint32_t stp = stage0 + (uint32_t)(s * kStageBytes);
-        const int tokbase = (it.tile0 + c.t) * kTile;
-        const uint32_t pm = mi.page_mask[s];
-        auto row_ok = [&](int r) { return tokbase + r < it.c1 && ((pm >> (r >> lgbs)) & 1u) != 0; };
-        const uint4 fw = *reinterpret_cast<const uint4*>(&mi.rowflag[s][part][0]);
-        uint32_t m[4] = {fw.x, fw.y, fw.z, fw.w};
-        const uint4 lastrow = lds128(stp + swz(kTile - 1, c8));   // this tile's last row before any rewrite: the next tile's left neighbour
-        if (m[0] | m[1] | m[2] | m[3]) {
-          uint32_t nx[4] = {0, 0, 0, 0};
-          bool nx_ok = false;
-          if (m[3] >> 31) {   // the tile's last row needs the row after it
-            if (c.t + 1 < it.ntiles) {
-              const int sn = (c.n + 1) % kStages;
-              mbar_wait(part ? &mi.vdec[sn] : &mi.kdec[sn], ((c.n + 1) / kStages) & 1);
-              const uint4 x = lds128(stage0 + (uint32_t)(sn * kStageBytes) + swz(0, c8));
-              nx[0] = x.x & M0F; nx[1] = x.y & M0F; nx[2] = x.z & M0F; nx[3] = x.w & M0F;
-              nx_ok = tokbase + kTile < it.c1 && (mi.page_mask[sn] & 1u) != 0;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) nx[k] = hdn[k];
-              nx_ok = hdn_ok;
-            }
-          }
-          int last_r = -2;               // last row of the previous group (already rewritten in shared memory) ...
-          uint32_t last_pre[4] = {0, 0, 0, 0};   // ... and its pre-interpolation nibbles
-          while (m[0] | m[1] | m[2] | m[3]) {
-            int rs[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {   // the four lowest flagged rows, ascending
-              int r = -1;
-              if (m[0]) { r = __ffs(m[0]) - 1; m[0] &= m[0] - 1; }
-              else if (m[1]) { r = 32 + __ffs(m[1]) - 1; m[1] &= m[1] - 1; }
-              else if (m[2]) { r = 64 + __ffs(m[2]) - 1; m[2] &= m[2] - 1; }
-              else if (m[3]) { r = 96 + __ffs(m[3]) - 1; m[3] &= m[3] - 1; }
-              rs[k] = r;
-            }
-            const int r = grp == 0 ? rs[0] : grp == 1 ? rs[1] : grp == 2 ? rs[2] : rs[3];
-            uint4 self = make_uint4(0, 0, 0, 0);
-            uint32_t up[4] = {0, 0, 0, 0}, dn[4] = {0, 0, 0, 0};
-            bool upok = false, dnok = false;
-            if (r >= 0) {
-              self = lds128(stp + swz(r, c8));
-              if (r == 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) up[k] = prev[k];
-                upok = prev_ok;
-              } else if (r - 1 == last_r) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) up[k] = last_pre[k];
-                upok = row_ok(r - 1);
-              } else {
-                const uint4 x = lds128(stp + swz(r - 1, c8));
-                up[0] = x.x & M0F; up[1] = x.y & M0F; up[2] = x.z & M0F; up[3] = x.w & M0F;
-                upok = row_ok(r - 1);
-              }
-              if (r == kTile - 1) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) dn[k] = nx[k];
-                dnok = nx_ok;
-              } else {
-                const uint4 x = lds128(stp + swz(r + 1, c8));
-                dn[0] = x.x & M0F; dn[1] = x.y & M0F; dn[2] = x.z & M0F; dn[3] = x.w & M0F;
-                dnok = row_ok(r + 1);
-              }
-            }
-            __syncwarp();   // every read of this group precedes its writes: neighbours are pre-interpolation values (no cascade)
-            const uint32_t sw[4] = {self.x, self.y, self.z, self.w};
-            uint32_t nw[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t sn4 = sw[k] & M0F;
-              const uint32_t l4 = upok ? up[k] : sn4, r4 = dnok ? dn[k] : sn4;   // a missing neighbour is replaced by the value itself
-              nw[k] = interp4(sn4, l4, r4, (sw[k] >> 7) & M01);
-            }
-            last_r = rs[3];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) last_pre[k] = __shfl_sync(0xFFFFFFFFu, sw[k] & M0F, 24 + c8);
-            if (r >= 0) sts128(stp + swz(r, c8), make_uint4(nw[0], nw[1], nw[2], nw[3]));
-            __syncwarp();
-          }
-          if (lane < 4) mi.rowflag[s][part][lane] = 0;
-          fence_async_smem();
-        }
-        prev[0] = lastrow.x & M0F; prev[1] = lastrow.y & M0F; prev[2] = lastrow.z & M0F; prev[3] = lastrow.w & M0F;
-        prev_ok = row_ok(kTile - 1);
-      }
-      if (part == 0) {
-        if (c.t == 0) mbar_wait(&mi.qready[(c.j % kQBufs)], (c.j / kQBufs) & 1);
-        mbar_wait(&mi.sfree[b], ((c.n >> 1) & 1) ^ 1);          // S(n-2) has been read out of this TMEM buffer
-      } else {
-        mbar_wait(&mi.wready[b], (c.n >> 1) & 1);               // W(n) and its fresh flag are in shared memory
-      }
-      __syncwarp();
-      if (lane == 0) {
-        TC_TRACE(c.n, part ? EV_PV_ISSUE : EV_S_ISSUE);
-        tc_after();
-        if (part == 0) {
-          const int qb = c.j % kQBufs;
-          const uint64_t ka = kdesc0 + (uint64_t)(s * (kStageBytes >> 4)), qa = qdesc0 + (uint64_t)(qb * (kQopBytes >> 4));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_i8(tmem + b * 16, ka + 2 * k, qa + 2 * k, kIdescS, k > 0);
-          tc_commit(&mi.sready[b]);
-        } else {
-          const uint32_t keep = mi.pv_fresh[b] ? 0u : 1u;
-          const uint64_t va = vdesc0 + (uint64_t)(s * (kStageBytes >> 4)), wa = wdesc0 + (uint64_t)(b * (kWBytes >> 4));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_i8(tmem + 32, va + 256 * k, wa + 32 * k, kIdescO, k > 0 ? 1u : keep);
-          tc_commit(&mi.oready[b]);
-          tc_commit(&mi.empty[s]);
-        }
-      }
-      __syncwarp();
-    }
-    if (part == 1 && lane == 0)
-      for (int back = min(c.n, kStages); back > 0; --back) mbar_wait(&mi.empty[(c.n - back) % kStages], ((c.n - back) / kStages) & 1);
   } else if (warp == 1 || warp == 3) {
     // =============================================================== MMA issuers (one thread each): role 1 = QK^T, role 3 = PV
     // Two independent issue streams: S(n) goes out as soon as the K half of tile n is decoded and its TMEM buffer has been
@@ -574,7 +405,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
           if (c.t == 0) mbar_wait(&mi.qready[qb], (c.j / kQBufs) & 1);
           mbar_wait(&mi.sfree[b], ((c.n >> 1) & 1) ^ 1);          // S(n-2) has been read out of this TMEM buffer
           TC_TRACE(c.n, EV_S_WAITK);
-          mbar_wait(&mi.kdec[s], (c.n / kStages) & 1);
+          mbar_wait(INTERP ? &mi.kfix[s] : &mi.kdec[s], (c.n / kStages) & 1);
           TC_TRACE(c.n, EV_S_ISSUE);
           tc_after();
           const uint64_t ka = kdesc0 + (uint64_t)(s * (kStageBytes >> 4)), qa = qdesc0 + (uint64_t)(qb * (kQopBytes >> 4));
@@ -586,7 +417,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
         for (; c.valid; advance(c)) {
           const int s = c.n % kStages, b = c.n & 1;
           mbar_wait(&mi.wready[b], (c.n >> 1) & 1);               // W(n) and its fresh flag are in shared memory
-          mbar_wait(&mi.vdec[s], (c.n / kStages) & 1);
+          mbar_wait(INTERP ? &mi.vfix[s] : &mi.vdec[s], (c.n / kStages) & 1);
           TC_TRACE(c.n, EV_PV_ISSUE);
           tc_after();
           const uint32_t keep = mi.pv_fresh[b] ? 0u : 1u;          // accumulate onto the previous tiles' product, or start over
@@ -887,6 +718,93 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
     }
     const uint32_t stage0 = sptr(sm + kOffStages);
     FlagCount fc;
+    // ---- INTERP: rewrite of the flagged cells of one (part, 16-byte column chunk) of a tile, after the tile's V part
+    static_assert(!INTERP || NDEC == 16, "one worker warp per (part, 16-byte column chunk)");
+    auto patch_chunk = [&](int s, int wpart, int wc, int wseq, int wkvh, int wc1, int wtokbase) {
+          const uint32_t st = stage0 + (uint32_t)(s * kStageBytes);
+          const uint4 bm4 = *reinterpret_cast<const uint4*>(&mi.colflag[s][wpart][wc][0]);
+          if (bm4.x | bm4.y | bm4.z | bm4.w) {
+            const uint32_t stp = st + (uint32_t)(wpart * kPartBytes);
+            const uint32_t pmw = mi.page_mask[s];
+            const int ctx = min(a.context_lens[wseq], a.max_blocks * bs);
+            const unsigned char* cache = wpart ? a.g.v_cache : a.g.k_cache;
+            // pre-interpolation nibbles of chunk wc of token `tok`, straight from the cache (neighbour outside the tile)
+            auto fetch = [&](int tok, uint32_t (&o)[4]) -> bool {
+              if (tok < 0 || tok >= ctx) return false;
+              const int blk = a.block_table[(int64_t)wseq * a.max_blocks + (tok >> lgbs)];
+              if (blk < 0) return false;
+              const uint4 xr = *reinterpret_cast<const uint4*>(
+                  cache + ((int64_t)(blk * (a.g.L * a.g.H) + a.layer * a.g.H + wkvh) * bs + (tok & (bs - 1))) * kD + wc * 16);
+              uint32_t fl;
+              hamming_decode4<ECCQ_CODEC_H84>(xr.x, o[0], fl); hamming_decode4<ECCQ_CODEC_H84>(xr.y, o[1], fl);
+              hamming_decode4<ECCQ_CODEC_H84>(xr.z, o[2], fl); hamming_decode4<ECCQ_CODEC_H84>(xr.w, o[3], fl);
+              return true;
+            };
+            auto row_ok = [&](int r) { return wtokbase + r < wc1 && ((pmw >> (r >> lgbs)) & 1u) != 0; };
+            uint32_t carry[4] = {0, 0, 0, 0};   // pre-interpolation nibbles of row 32 q - 1 when the previous group rewrote it
+            bool carry_set = false;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t bmq = q == 0 ? bm4.x : q == 1 ? bm4.y : q == 2 ? bm4.z : bm4.w;
+              if (bmq == 0) { carry_set = false; continue; }
+              const int r = 32 * q + lane;
+              const bool mine = (bmq >> lane) & 1u;
+              uint32_t sw[4] = {0, 0, 0, 0}, up[4] = {0, 0, 0, 0}, dn[4] = {0, 0, 0, 0};
+              bool upok = false, dnok = false;
+              if (mine) {
+                const uint4 x = lds128(stp + swz(r, wc));
+                sw[0] = x.x; sw[1] = x.y; sw[2] = x.z; sw[3] = x.w;
+                if (r == 0) {
+                  upok = fetch(wtokbase - 1, up);
+                } else if (lane == 0 && carry_set) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) up[k] = carry[k];
+                  upok = row_ok(r - 1);
+                } else {
+                  const uint4 u = lds128(stp + swz(r - 1, wc));
+                  up[0] = u.x & M0F; up[1] = u.y & M0F; up[2] = u.z & M0F; up[3] = u.w & M0F;
+                  upok = row_ok(r - 1);
+                }
+                if (r == kTile - 1) {
+                  dnok = fetch(wtokbase + kTile, dn);
+                } else {
+                  const uint4 d = lds128(stp + swz(r + 1, wc));
+                  dn[0] = d.x & M0F; dn[1] = d.y & M0F; dn[2] = d.z & M0F; dn[3] = d.w & M0F;
+                  dnok = row_ok(r + 1);
+                }
+              }
+              __syncwarp();   // every read of the group precedes its writes
+              carry_set = (bmq >> 31) & 1u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) carry[k] = __shfl_sync(0xFFFFFFFFu, sw[k] & M0F, 31);
+              if (mine) {
+                uint32_t nw[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t sn4 = sw[k] & M0F;
+                  nw[k] = interp4(sn4, upok ? up[k] : sn4, dnok ? dn[k] : sn4, (sw[k] >> 7) & M01);   // a missing neighbour = the value itself
+                }
+                sts128(stp + swz(r, wc), make_uint4(nw[0], nw[1], nw[2], nw[3]));
+              }
+              __syncwarp();
+            }
+            if (lane < 4) mi.colflag[s][wpart][wc][lane] = 0;
+            fence_async_smem();
+          }
+          __syncwarp();
+    };
+    // Run by every decode warp after the tile's V part: warps 0-7 own K chunk dw (every warp stored its K rows a part ago, so
+    // their wait is over), warps 8-15 V chunk dw - 8 (they wait for the slowest warp's V rows: 12 % of the kernel's stall samples).
+    // Measured alternatives, both slower: the V rewrite deferred until after the next tile's K part (0.42 ms vs 0.29 ms), ONE
+    // rotating V worker per tile that checks all eight chunks (0.38 ms) -- the later the PV issuer's barrier completes, the
+    // longer the stage is held.
+    auto worker = [&](int wn, int wseq, int wkvh, int wc1, int wtokbase) {
+      const int s = wn % kStages;
+      const int wpart = dw >> 3;
+      mbar_wait(wpart ? &mi.vdec[s] : &mi.kdec[s], (wn / kStages) & 1);   // every row of the part is stored (marks included)
+      patch_chunk(s, wpart, dw & 7, wseq, wkvh, wc1, wtokbase);
+      if (lane == 0) mbar_arrive(wpart ? &mi.vfix[s] : &mi.kfix[s]);
+    };
     int n = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       Item it;
@@ -933,7 +851,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
               }
               if (any) {
                 const int row = (dw + i * NDEC) * 4 + (lane >> 3);
-                atomicOr(&mi.rowflag[s][part][row >> 5], 1u << (row & 31));
+                atomicOr(&mi.colflag[s][part][lane & 7][row >> 5], 1u << (row & 31));
               }
               y0 = y4[0]; y1 = y4[1]; y2 = y4[2]; y3 = y4[3];
             } else {
@@ -948,6 +866,9 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
           __syncwarp();
           if (lane == 0) mbar_arrive(part == 0 ? &mi.kdec[s] : &mi.vdec[s]);
           if (dw == 0 && lane == 0) TC_TRACE(n, part == 0 ? EV_DEC_K : EV_DEC_V);
+        }
+        if constexpr (INTERP) {
+          worker(n, it.seq, it.kvh, it.c1, tokbase);
         }
       }
     }

@@ -121,6 +121,37 @@ def paged_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_sc
     return out if out.dtype == query.dtype else out.to(query.dtype)
 
 
+def paged_prefill_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_scales, v_scales, layer_idx, block_size,
+                                sm_scale=None, codec="hamming84", *, use_interpolation=False, counters=None):
+    """ECC-fused causal prefill attention: query [B, Hq, Sq, D] -> [B, Hq, Sq, D] in query.dtype, straight from the codeword
+    pages (the decode + interpolation + dequantisation of ECCBackend.attend, kv_cache/ecc_shim.py:979-1089, and the causal
+    SDPA of `_run_attention`, :1138-1164, in one kernel; no K/V tensor is materialised).  block_table [nseq, max_blocks],
+    context_lens [nseq] with nseq == B, or nseq == 1 for one context shared by all B query rows (the reference's batch
+    semantics).  Query t sits at position context_len - Sq + t."""
+    assert query.is_cuda, "Query must be on CUDA"
+    if codec not in ("hamming84", "hamming74", "golay", "int4"):
+        raise ValueError(f"Unknown codec: {codec}")
+    B, Hq, Sq, D = query.shape
+    qd = query if query.dtype in (torch.float32, torch.float16, torch.bfloat16) else query.float()
+    qd = qd.contiguous()
+    if sm_scale is None:
+        sm_scale = 1.0 / math.sqrt(D)
+    bt = block_table.to(torch.int32).contiguous()
+    if bt.dim() == 1:
+        bt = bt.unsqueeze(0)
+    cl = context_lens.to(torch.int32).contiguous()
+    nseq = bt.shape[0]
+    if nseq not in (1, B):
+        raise ValueError(f"block_table rows ({nseq}) must be 1 or the query batch ({B})")
+    desc = _lib.cache_desc(k_cache, v_cache, k_scales, v_scales, D, block_size, codec)
+    out = torch.empty_like(qd)
+    with device_of(qd):
+        check(load().eccq_paged_prefill_attention(desc, ptr(qd), ptr(out), _lib.dtype_code(qd.dtype), ptr(bt), bt.shape[1], ptr(cl), nseq, B,
+                                                  Hq, Sq, int(layer_idx), float(sm_scale), int(bool(use_interpolation) and codec == "hamming84"),
+                                                  int(counters is not None), ptr(counters), stream_of(qd)), "paged_prefill_attention_ecc")
+    return out if out.dtype == query.dtype else out.to(query.dtype)
+
+
 def read_cache(k_cache, v_cache, k_scales, v_scales, block_table, context_lens, layer_idx, block_size, head_dim, codec,
                use_interpolation=False, out_dtype=torch.float32, counters=None, return_nibbles=False, max_context=None, out=None):
     """Fused gather + decode + [interpolate] + dequantise of whole contexts: returns K, V

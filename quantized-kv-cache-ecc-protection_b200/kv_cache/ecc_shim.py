@@ -18,6 +18,7 @@ There is no Triton, no dispatch to other backends and no CPU fallback in this pa
 from __future__ import annotations
 
 import math
+import os
 from contextlib import contextmanager
 
 import torch
@@ -27,7 +28,11 @@ import torch.nn.functional as F
 from .. import _lib
 from .._lib import (CTR_CORRECTED, CTR_DETECTED, CTR_FLIPPED, CTR_INTERPOLATED, INJECT_MASK, INJECT_MODES, INJECT_NONE, check,
                     device_of, load, new_counters, ptr, stream_of)
-from .attention_ecc import paged_attention_ecc, read_cache
+from .attention_ecc import paged_attention_ecc, paged_prefill_attention_ecc, read_cache
+
+# Longest context served by the fused causal prefill kernel (CUDA-core dot products: every token row is decoded once per
+# block of 8 queries); beyond it the attention is GEMM-shaped and goes through the fused read + the library's flash SDPA.
+_PREFILL_FUSED_MAX_CTX = int(os.environ.get("ECCQ_PREFILL_FUSED_MAX_CTX", "2048"))
 
 
 def compute_injection_seed(base_seed: int, layer_idx: int, injection_count: int) -> int:
@@ -338,6 +343,12 @@ class ECCBackend:
             if shared:
                 out = out.reshape(self.num_kv_heads, B, G, D).permute(1, 0, 2, 3).reshape(B, Hq, D)
             return out.unsqueeze(2)
+        if max(lens) <= _PREFILL_FUSED_MAX_CTX and D <= 256:
+            # ECC-fused causal prefill: ONE hand-written kernel consumes the codeword pages (decode + interpolation in the K/V
+            # prologue, fp32 online softmax); no K/V tensor is materialised and no library attention kernel runs
+            return paged_prefill_attention_ecc(q, m.k_cache, m.v_cache, bt, cl, m.k_scales, m.v_scales, layer_idx, m.block_size,
+                                               codec=cfg.codec, use_interpolation=cfg.use_interpolation, counters=self._counters)
+        # long contexts: the contraction is GEMM-shaped work for the library's flash kernels (fused read -> K/V in q's dtype -> SDPA)
         dt = q.dtype if q.dtype in (torch.float32, torch.float16, torch.bfloat16) else torch.float32
         k, v = read_cache(m.k_cache, m.v_cache, m.k_scales, m.v_scales, bt, cl, layer_idx, m.block_size, D, cfg.codec,
                           use_interpolation=cfg.use_interpolation, out_dtype=dt, counters=self._counters, max_context=max(lens))

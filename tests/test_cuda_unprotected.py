@@ -73,7 +73,7 @@ def test_unprotected_backend(golden, ber):
 
 def test_unprotected_patch_and_stats():
     """patch_model_with_unprotected_attention / reset / stats on a random-init 2-layer GPT-2: BER 0 reproduces the int4 ECC-shim
-    mode exactly (same quantiser, same storage, top-left causal mask), BER > 0 flips about ber * total_bits bits."""
+    mode (same quantiser, same storage, top-left causal mask), BER > 0 flips about ber * total_bits bits."""
     from transformers import GPT2Config, GPT2LMHeadModel
     from eccq_b200.kv_cache import (ECCShimConfig, UnprotectedShimConfig, get_unprotected_stats, patch_model_with_ecc_attention,
                                     patch_model_with_unprotected_attention, reset_ecc_cache, reset_unprotected_cache)
@@ -89,7 +89,8 @@ def test_unprotected_patch_and_stats():
             reset_unprotected_cache(model)
             out = model(ids).logits
             st = get_unprotected_stats(model)
-        assert torch.equal(out, ref)
+        # same cache image, same arithmetic; the ECC shim's prefill runs in the fused kernel, this one through SDPA: fp32 rounding apart
+        assert torch.allclose(out, ref, atol=2e-5, rtol=1e-5)
         assert st == {"allocated_blocks": 3, "free_blocks": 5, "sequences": 1, "injection_count": 0, "bits_flipped": 0, "total_bits": 0,
                       "actual_ber": 0.0}
         with patch_model_with_unprotected_attention(model, UnprotectedShimConfig(ber=0.02, inject_errors=True, block_size=16, num_blocks=8),
