@@ -347,7 +347,10 @@ __device__ __forceinline__ void fast_flip_positions(const FastInject& fi, uint64
 // OR-ed into its slot's mask in shared memory (SW words per slot, zero on entry).  The first position past the window is
 // carried into the next window (later draws are discarded: the process is memoryless).  At BER 1e-2 a 4-iteration window
 // of Hamming(8,4) rows holds ~330 flips = 3 rounds; the cost per value is a quarter of the per-iteration scheme's.
-constexpr int kInjWindow = 4;
+#ifndef ECCQ_INJ_WINDOW
+#define ECCQ_INJ_WINDOW 4
+#endif
+constexpr int kInjWindow = ECCQ_INJ_WINDOW;
 struct GapRng4 {
   uint32_t ctr, c0, c1, k0, k1;
   uint32_t spare0, spare1;   // upper halves of the last Philox call (every call feeds two rounds)

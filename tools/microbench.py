@@ -32,14 +32,19 @@ def timeit(name, fn, nbytes, reps=20, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    # median over batches of back-to-back launches between one event pair, like bench.py's timed region and the reference's
+    # cuda_timer (round 1 timed isolated launches with a host sync in between: every launch then starts on an idle GPU, which
+    # cost the injecting write 0.231 ms here against 0.194 ms in the bench -- the disagreement the round-1 review pointed at)
     ts = []
-    for _ in range(reps):
+    per = max(1, reps // 4)
+    for _ in range(5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        for _ in range(per):
+            fn()
         b.record()
         b.synchronize()
-        ts.append(a.elapsed_time(b))
+        ts.append(a.elapsed_time(b) / per)
     ms = statistics.median(ts)
     gbs = nbytes / (ms * 1e-3) / 1e9
     RESULTS.append({"kernel": name, "ms": ms, "gbs": gbs, "frac": gbs / PEAK})
