@@ -506,8 +506,8 @@ def run_ours(args):
 
     if rank == 0:
         cb = None
-        if not args.no_cpu:
-            cb = cpu_leg(3, 1, min_seconds=8.0)   # ~8 s of host work
+        if not args.no_cpu and world == 1:        # the CPU baseline is an N = 1 record (at N > 1 the other ranks' barrier polling
+            cb = cpu_leg(3, 1, min_seconds=8.0)   # shares rank 0's cores: 7.3 GB/s at N = 8 against 21.6 GB/s alone); ~8 s of host work
             cb["c1"] = cpu_c1()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8",
