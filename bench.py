@@ -588,6 +588,23 @@ def bench_attention(torch, dev, lib, _lib, paged_attention_ecc, SimpleBlockManag
         variants["error"] = repr(exc)
     finally:
         os.environ.pop("ECCQ_ATTN_INTERP_TWO_PASS", None)
+    # Golay(24,12) cache of the same shard (43 codewords per row, 1.34 B per value): one pass of the tcgen05 kernel
+    try:
+        del m
+        torch.cuda.empty_cache()
+        mg = SimpleBlockManager(nblk, BS, 1, HKV, D, device=dev, codec="golay")
+        mg.block_table = torch.randperm(nblk, generator=torch.Generator().manual_seed(3)).to(torch.int32).view(Bq, nblk_seq).to(dev)
+        for s0 in range(0, ctx, chunk):
+            kk = torch.randn(Bq, chunk, HKV * D, device=dev, dtype=torch.float16)
+            start = torch.full((Bq,), s0, dtype=torch.int32, device=dev)
+            _lib.check(lib.eccq_cache_write(mg.desc(), P(kk), P(kk.flip(1)), _lib.ECCQ_F16, P(mg.block_table), nblk_seq, P(start), Bq, chunk, 0,
+                                            _lib.INJECT_PHILOX_FAST, None, None, 1e-3, 1, s0, None, sp), "cache_write")
+        gbytes = Bq * ctx * (2 * HKV * 4 * ((D + 2) // 3) + 2 * HKV * 4)
+        ms_g = timed(lambda: paged_attention_ecc(q, mg.k_cache, mg.v_cache, mg.block_table, cl, mg.k_scales, 0, BS, codec="golay", v_scales=mg.v_scales))
+        variants["golay_single_pass"] = {"ms": ms_g, "roofline_frac": gbytes / (ms_g * 1e-3) / 1e9 / peak, "algorithmic_bytes": gbytes}
+        del mg
+    except Exception as exc:
+        variants["golay_error"] = repr(exc)
     return {"workload": "C5 shard: batch 8 x 32768 ctx, Hq 32, Hkv 8, D 128, block 16, Hamming(8,4), q_len 1, one layer",
             "cache_fill_ber": 1e-3, "variants": variants,
             "ms_per_layer_call": ms, "context_tokens_per_s_per_gpu": Bq * ctx / (ms * 1e-3),

@@ -361,7 +361,9 @@ static int run_attn(const CacheGeom& g, const AttnArgs& a_in, uint64_t* counters
       return ECCQ_OK;
     }
   }
-  if (!a.force_general && try_attn_mma<TQ>(g, a, counters, st)) {
+  const int took_mma = a.force_general ? 0 : try_attn_mma<TQ>(g, a, counters, st);
+  if (took_mma < 0) return took_mma;
+  if (took_mma) {
     dim3 mg0(a.Hq, a.nseq);
     attn_merge_kernel<TQ><<<mg0, 128, 0, st>>>(a.ws, reinterpret_cast<TQ*>(a.out), a.Hq, g.D, a.nsplit);
     return ECCQ_OK;

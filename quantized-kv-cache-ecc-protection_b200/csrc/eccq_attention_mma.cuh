@@ -427,29 +427,30 @@ static int launch_attn_mma(const CacheGeom& g, AttnArgs& a, uint64_t* counters, 
       const size_t upper = std::max<size_t>((kLutWarps - kLutLowWarps) * 2 * stage, sizeof(float) * kLutWarps * 8 * (D + 2));
       const size_t smem = 0x20000 + upper;
       const int items = a.nsplit * g.H * npass * a.nseq;
-      auto go = [&](auto kern) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      auto go = [&](auto kern) -> int {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
         kern<<<std::min(items, sm_count()), kLutWarps * 32, smem, st>>>(g, a, counters, tab);
+        return check_launch("paged_decode_attention (mma.sync, table prologue)");
       };
       constexpr int HC = kHamming ? CODEC : ECCQ_CODEC_H84;
-      if (lut_env == 2) go(attn_mma_kernel<TQ, HC, D, PRECISE, false, 2>);
-      else if (lut_env == 3) go(attn_mma_kernel<TQ, HC, D, PRECISE, false, 3>);
-      else go(attn_mma_kernel<TQ, HC, D, PRECISE, false, 1>);
-      return ECCQ_OK;
+      if (lut_env == 2) return go(attn_mma_kernel<TQ, HC, D, PRECISE, false, 2>);
+      if (lut_env == 3) return go(attn_mma_kernel<TQ, HC, D, PRECISE, false, 3>);
+      return go(attn_mma_kernel<TQ, HC, D, PRECISE, false, 1>);
     }
   }
   const size_t smem = std::max<size_t>(kMmaWarps * 2 * stage, sizeof(float) * kMmaWarps * 8 * (D + 2));
   dim3 grid(a.nsplit, g.H * npass, a.nseq);
-  if (a.count_errors) {
-    auto kern = attn_mma_kernel<TQ, CODEC, D, PRECISE, true, 0>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto go = [&](auto kern) -> int {
+    if (smem > 48 * 1024) {
+      const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
+    }
     kern<<<grid, kMmaThreads, smem, st>>>(g, a, counters, nullptr);
-  } else {
-    auto kern = attn_mma_kernel<TQ, CODEC, D, PRECISE, false, 0>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kMmaThreads, smem, st>>>(g, a, counters, nullptr);
-  }
-  return ECCQ_OK;
+    return check_launch("paged_decode_attention (mma.sync)");
+  };
+  if (a.count_errors) return go(attn_mma_kernel<TQ, CODEC, D, PRECISE, true, 0>);
+  return go(attn_mma_kernel<TQ, CODEC, D, PRECISE, false, 0>);
 }
 
 // returns 1 when the tile kernel took the launch, 0 when the shape/codec needs the general kernel
@@ -460,9 +461,11 @@ static int try_attn_mma(const CacheGeom& g, AttnArgs& a, uint64_t* counters, cud
   if (!aligned16(g.k_cache) || !aligned16(g.v_cache) || !aligned16(g.k_scales) || !aligned16(g.v_scales)) return 0;
   constexpr bool PRECISE = sizeof(TQ) == 4;
 #define ECCQ_MMA_CASE(C)                                                                       \
-  if (g.D == 128) launch_attn_mma<TQ, C, 128, PRECISE>(g, a, counters, st);                    \
-  else launch_attn_mma<TQ, C, 64, PRECISE>(g, a, counters, st);                                \
-  return 1
+  {                                                                                            \
+    const int rc = g.D == 128 ? launch_attn_mma<TQ, C, 128, PRECISE>(g, a, counters, st)       \
+                              : launch_attn_mma<TQ, C, 64, PRECISE>(g, a, counters, st);       \
+    return rc ? rc : 1;   /* 1 = took the launch, < 0 = error */                               \
+  }
   switch (g.codec) {
     case ECCQ_CODEC_H84: ECCQ_MMA_CASE(ECCQ_CODEC_H84);
     case ECCQ_CODEC_H74: ECCQ_MMA_CASE(ECCQ_CODEC_H74);

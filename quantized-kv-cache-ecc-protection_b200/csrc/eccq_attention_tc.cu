@@ -25,6 +25,12 @@
 //               at the 128-byte-swizzled position the UMMA descriptors expect
 // Partials (acc[D], m, l) per split go through the same workspace / attn_merge_kernel as the other attention kernels.
 //
+// Golay(24,12) caches (CODEC = ECCQ_CODEC_GOLAY, 43 codewords of 3 nibbles per 128-dim row) run in the same pipeline in
+// ONE pass: a 2 752-byte Golay page cannot be decoded in place into a 2 048-byte operand page, so the producers only stage the
+// scales and every decode warp reads the codewords of its eight token rows straight from the cache in global memory (one
+// contiguous 1 376-byte run per part, the next tile's words in flight while this tile is decoded), corrects them with the
+// 4 096-entry syndrome table held in shared memory and writes the nibbles into the tile at the swizzled byte positions.
+//
 // Temporal interpolation of double-detected values (ECCShimConfig.use_interpolation, kv_cache/ecc_shim.py:1038-1059 +
 // interpolation_triton.py:120-159) runs in the SAME pass (template parameter INTERP): the decode warps leave bit 7 set on every
 // double-detected byte and set bit (row) of their 16-byte column chunk's bitmap.  Interpolation runs along the token axis at a
@@ -81,7 +87,9 @@ struct Misc {
   uint32_t pv_fresh[2];                  // 1: PV of this weight buffer starts a new accumulation in TMEM (written before wready)
   uint32_t tmem_base;
 };
-constexpr int kSmemBytes = kOffMisc + (int)sizeof(Misc) + 1024;   // + alignment slack
+constexpr int kOffGolay = (kOffMisc + (int)sizeof(Misc) + 15) / 16 * 16;   // Golay variant: 4096 x u16 syndrome table + 2 x 64 x u16 parity tables
+constexpr int kGolayBytes = 4096 * 2 + 2 * 64 * 2;
+constexpr int kSmemBytes = kOffGolay + kGolayBytes + 1024;   // + alignment slack
 
 struct alignas(64) Args {
   // 2-D tensor maps for tile::gather4: K / V caches as rows of 2048 bytes (256 x u64), scales as rows of block_size floats
@@ -284,6 +292,17 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
     for (int i = 0; i < kStages * 2 * 8 * 4; ++i) (&mi.colflag[0][0][0][0])[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  constexpr bool kGolay = CODEC == ECCQ_CODEC_GOLAY;
+  uint16_t* const g_syn = reinterpret_cast<uint16_t*>(sm + kOffGolay);      // data-bit error pattern | weight << 12 | uncorrectable << 15
+  uint16_t* const g_lo = g_syn + 4096;
+  uint16_t* const g_hi = g_lo + 64;
+  if (kGolay) {
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) {
+      const int32_t pat = g_golay.syn[i];
+      g_syn[i] = pat < 0 ? (uint16_t)0x8000u : (uint16_t)((pat & 0xFFF) | (__popc(pat) << 12));
+    }
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) { g_lo[i] = g_golay.par_lo[i]; g_hi[i] = g_golay.par_hi[i]; }
+  }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(sptr(&mi.tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -355,9 +374,13 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
           mbar_wait(&mi.empty[s], ((n / kStages) & 1) ^ 1);
           TC_TRACE(n, part ? EV_LOAD_V : EV_LOAD_ISSUE);
           if (part == 0) mi.page_mask[s] = (vm32 >> (8 * ti)) & 0xFFu;
-          mbar_arrive_tx(&mi.full[s], (uint32_t)(kPartBytes + kTile * 4));
-          tma_gather4(st + part * kPartBytes, tm_c, ra.x, ra.y, ra.z, ra.w, &mi.full[s]);
-          tma_gather4(st + part * kPartBytes + 8192, tm_c, rb.x, rb.y, rb.z, rb.w, &mi.full[s]);
+          if (kGolay) {
+            mbar_arrive_tx(&mi.full[s], (uint32_t)(kTile * 4));      // scales only: the decode warps fetch the codewords themselves
+          } else {
+            mbar_arrive_tx(&mi.full[s], (uint32_t)(kPartBytes + kTile * 4));
+            tma_gather4(st + part * kPartBytes, tm_c, ra.x, ra.y, ra.z, ra.w, &mi.full[s]);
+            tma_gather4(st + part * kPartBytes + 8192, tm_c, rb.x, rb.y, rb.z, rb.w, &mi.full[s]);
+          }
           unsigned char* sdst = st + 2 * kPartBytes + part * kTile * 4;
           if (ppt == 8) {
             tma_gather4(sdst, tm_s, ra.x, ra.y, ra.z, ra.w, &mi.full[s]);
@@ -810,6 +833,94 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       Item it;
       if (!get_item(a, item, it)) continue;
       const bool do_count = COUNT && it.pass == 0;
+      if constexpr (kGolay) {
+        // ---- Golay: rows 8 dw .. 8 dw + 7 of every tile.  A work item is (row, group g of four codewords 4g .. 4g+3) = twelve
+        // nibbles = dims 12g .. 12g+11 = THREE aligned 32-bit words of the operand row, each inside one 16-byte chunk (so the
+        // swizzle never splits a word); group 10 is the row's tail (codewords 40-42, dims 120-127, two words).  88 items per
+        // part and warp = 3 warp iterations.  The four codewords of an item are four 32-bit loads from the cache (stride 16 B
+        // across the lanes: the four loads of an iteration touch every byte of the warp's 1 376-byte run once, L1 serves the
+        // sectors); as soon as a part is decoded its register set is reloaded with the same part of the NEXT tile.
+        static_assert(!kGolay || NDEC == 16, "eight token rows per decode warp");
+        constexpr int CW = (kD + 2) / 3, GPR = 11, NITEM = 8 * GPR, NIT = (NITEM + 31) / 32;
+        const int r0 = 8 * dw;
+        const int LHg = a.g.L * a.g.H, lh0g = a.layer * a.g.H;
+        uint32_t ncorr = 0, ndet = 0;
+        uint32_t wk[NIT][4], wv[NIT][4];
+        auto load_part = [&](int tt, const void* cache_base, uint32_t (&o)[NIT][4]) {
+          const int tok0 = (it.tile0 + tt) * kTile + r0;
+          const int lb = tok0 >> lgbs;
+          const int blk = (tt < it.ntiles && tok0 < it.c1 && lb < a.max_blocks) ? a.block_table[(int64_t)it.seq * a.max_blocks + lb] : -1;
+          const uint32_t* cache = reinterpret_cast<const uint32_t*>(cache_base) + ((int64_t)(blk * LHg + lh0g + it.kvh) * bs + (tok0 & (bs - 1))) * CW;
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const int item = i * 32 + lane;
+            const int rr = item / GPR, g = item - rr * GPR;
+            const bool in = blk >= 0 && item < NITEM;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[i][k] = (in && 4 * g + k < CW) ? __ldg(cache + rr * CW + 4 * g + k) : 0u;
+          }
+        };
+        auto decode_part = [&](int part, const uint32_t (&w)[NIT][4], uint32_t st, uint32_t pm, int tokbase) {
+#pragma unroll
+          for (int i = 0; i < NIT; ++i) {
+            const int item = i * 32 + lane;
+            if (item < NITEM) {
+              const int rr = item / GPR, g = item - rr * GPR;
+              const int row = r0 + rr;
+              const bool cnt = COUNT && do_count && tokbase + row < it.c1 && ((pm >> (row >> lgbs)) & 1u);
+              uint32_t sp[4];   // the three corrected nibbles of each codeword, one per byte
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t cw = w[i][k];
+                uint32_t d = cw & 0xFFFu;
+                const uint32_t syn = ((uint32_t)g_lo[d & 63u] ^ (uint32_t)g_hi[d >> 6]) ^ ((cw >> 12) & 0xFFFu);
+                const uint32_t e = g_syn[syn];
+                d ^= e & 0xFFFu;                               // uncorrectable words (bit 15) carry a zero pattern: data preserved
+                if (COUNT && cnt && 4 * g + k < CW) { if (e & 0x8000u) ++ndet; else ncorr += (e >> 12) & 7u; }
+                sp[k] = (d & 0xFu) | ((d & 0xF0u) << 4) | ((d & 0xF00u) << 8);
+              }
+              const uint32_t w0 = sp[0] | (sp[1] << 24), w1 = (sp[1] >> 8) | (sp[2] << 16), w2 = (sp[2] >> 16) | (sp[3] << 8);
+              const uint32_t rowbase = st + (uint32_t)(part * kPartBytes + row * 128);
+              const int d0 = 12 * g;                           // multiple of 4: every word lies inside one 16-byte chunk
+              const uint32_t sx = (uint32_t)(row & 7);
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(rowbase + ((((uint32_t)d0 >> 4) ^ sx) << 4) + ((uint32_t)d0 & 15u)), "r"(w0) : "memory");
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(rowbase + ((((uint32_t)(d0 + 4) >> 4) ^ sx) << 4) + ((uint32_t)(d0 + 4) & 15u)), "r"(w1) : "memory");
+              if (g < GPR - 1)
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(rowbase + ((((uint32_t)(d0 + 8) >> 4) ^ sx) << 4) + ((uint32_t)(d0 + 8) & 15u)), "r"(w2) : "memory");
+            }
+          }
+        };
+        load_part(0, a.g.k_cache, wk);
+        load_part(0, a.g.v_cache, wv);
+        for (int t = 0; t < it.ntiles; ++t, ++n) {
+          const int s = n % kStages;
+          const uint32_t st = stage0 + (uint32_t)(s * kStageBytes);
+          mbar_wait(&mi.full[s], (n / kStages) & 1);           // the stage is free (and its scales have landed)
+          if (dw == 0 && lane == 0) TC_TRACE(n, EV_DEC_START);
+          const uint32_t pm = COUNT ? mi.page_mask[s] : 0u;
+          const int tokbase = (it.tile0 + t) * kTile;
+          decode_part(0, wk, st, pm, tokbase);
+          load_part(t + 1, a.g.k_cache, wk);                   // the next tile's K words into the set just consumed
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mi.kdec[s]);
+          if (dw == 0 && lane == 0) TC_TRACE(n, EV_DEC_K);
+          decode_part(1, wv, st, pm, tokbase);
+          load_part(t + 1, a.g.v_cache, wv);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&mi.vdec[s]);
+          if (dw == 0 && lane == 0) TC_TRACE(n, EV_DEC_V);
+        }
+        if (COUNT) {
+          ncorr = __reduce_add_sync(0xFFFFFFFFu, ncorr); ndet = __reduce_add_sync(0xFFFFFFFFu, ndet);
+          if (lane == 0 && counters != nullptr) {
+            if (ncorr) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + ECCQ_CTR_CORRECTED, (unsigned long long)ncorr);
+            if (ndet) atomicAdd(reinterpret_cast<unsigned long long*>(counters) + ECCQ_CTR_DETECTED, (unsigned long long)ndet);
+          }
+        }
+        continue;
+      }
       for (int t = 0; t < it.ntiles; ++t, ++n) {
         const int s = n % kStages;
         const uint32_t st = stage0 + (uint32_t)(s * kStageBytes);
@@ -944,14 +1055,19 @@ extern "C" int eccq_tc_trace_read(long long* out_host) {
 // outside it, < 0 on error.  May lower a.nsplit / raise a.chunk (fewer, longer splits; the workspace was sized for more).
 int try_attn_tc(const CacheGeom& g, AttnArgs& a, int q_dtype, uint64_t* counters, cudaStream_t st) {
   static const int env = [] { const char* v = std::getenv("ECCQ_ATTN_TC"); return v && *v ? std::atoi(v) : 1; }();
-  if (!env || g.codec == ECCQ_CODEC_GOLAY || (a.interp && g.codec != ECCQ_CODEC_H84) || g.D != tc::kD) return 0;
+  static const int golay_env = [] { const char* v = std::getenv("ECCQ_ATTN_TC_GOLAY"); return v && *v ? std::atoi(v) : 1; }();
+  const bool golay = g.codec == ECCQ_CODEC_GOLAY;
+  if (!env || (golay && !golay_env) || (a.interp && g.codec != ECCQ_CODEC_H84) || g.D != tc::kD) return 0;
   if (g.bs < 16 || g.bs > tc::kTile || (tc::kTile % g.bs) != 0) return 0;
   if (!aligned16(g.k_cache) || !aligned16(g.v_cache) || !aligned16(g.k_scales) || !aligned16(g.v_scales)) return 0;
   const int G = a.Hq / g.H;
   tc::Args t;
   const uint64_t pages = (uint64_t)g.nb * g.L * g.H;
   if (pages * (uint64_t)(g.bs / 16) >= 0x7FFFFFFFull) return 0;
-  if (!tc::tensor_map_rows(t.tm_k, g.k_cache, pages * (g.bs / 16), 2048, 8) || !tc::tensor_map_rows(t.tm_v, g.v_cache, pages * (g.bs / 16), 2048, 8) ||
+  // Golay: the codewords are read by the decode warps themselves (no tensor map; the two slots alias the scale maps)
+  if ((!golay && (!tc::tensor_map_rows(t.tm_k, g.k_cache, pages * (g.bs / 16), 2048, 8) ||
+                  !tc::tensor_map_rows(t.tm_v, g.v_cache, pages * (g.bs / 16), 2048, 8))) ||
+      (golay && (!tc::tensor_map_rows(t.tm_k, g.k_scales, pages, (uint32_t)g.bs * 4, 4) || !tc::tensor_map_rows(t.tm_v, g.k_scales, pages, (uint32_t)g.bs * 4, 4))) ||
       !tc::tensor_map_rows(t.tm_ks, g.k_scales, pages, (uint32_t)g.bs * 4, 4) ||
       !tc::tensor_map_rows(t.tm_vs, a.v_use_k_scales ? g.k_scales : g.v_scales, pages, (uint32_t)g.bs * 4, 4))
     return 0;
@@ -972,7 +1088,9 @@ int try_attn_tc(const CacheGeom& g, AttnArgs& a, int q_dtype, uint64_t* counters
   int rc;
 #define ECCQ_TC_CASE(C, CNT)                                            \
   rc = ndec == 8 ? tc::launch<C, CNT, 8>(t, counters, st) : tc::launch<C, CNT, 16>(t, counters, st)
-  if (a.interp) {
+  if (golay) {
+    rc = a.count_errors ? tc::launch<ECCQ_CODEC_GOLAY, true, 16>(t, counters, st) : tc::launch<ECCQ_CODEC_GOLAY, false, 16>(t, counters, st);
+  } else if (a.interp) {
     rc = a.count_errors ? tc::launch<ECCQ_CODEC_H84, true, 16, true>(t, counters, st) : tc::launch<ECCQ_CODEC_H84, false, 16, true>(t, counters, st);
   } else if (a.count_errors) {
     switch (g.codec) {
@@ -992,3 +1110,5 @@ int try_attn_tc(const CacheGeom& g, AttnArgs& a, int q_dtype, uint64_t* counters
 }
 
 }  // namespace eccq
+
+ECCQ_DEFINE_TU_TABLES(attention_tc)

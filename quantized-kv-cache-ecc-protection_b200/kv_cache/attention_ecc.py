@@ -97,7 +97,10 @@ def paged_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_sc
         # their temporal neighbours inside the tile pipeline (csrc/eccq_attention_tc.cu, INTERP variant).
         single_pass = interp and D == 128 and block_size in (16, 32, 64, 128) and os.environ.get("ECCQ_ATTN_TC", "1") != "0" \
             and os.environ.get("ECCQ_ATTN_INTERP_TWO_PASS", "0") == "0"
-        if (interp and not single_pass) or codec == "golay":
+        # Golay at head_dim 128: also one pass (the decode warps of the tcgen05 kernel read the codewords from global memory)
+        golay_single = codec == "golay" and D == 128 and block_size in (16, 32, 64, 128) and os.environ.get("ECCQ_ATTN_TC", "1") != "0" \
+            and os.environ.get("ECCQ_ATTN_TC_GOLAY", "1") != "0"
+        if (interp and not single_pass) or (codec == "golay" and not golay_single):
             # temporal neighbours span pages (and Golay codewords span values): resolve them once with the streaming read
             # kernels into corrected INT4 pages (same paged layout, one layer), then attend over those with the INT4 tile
             # path.  Falls through to the general kernel for geometries the streaming kernels do not cover.

@@ -219,6 +219,43 @@ torch.save((out.cpu(), ctr.cpu()), sys.argv[1])
     assert c1.tolist() == c2.tolist() and c1[1] > 1000
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("bs", [16, 32, 64, 128])
+def test_golay_single_pass_block_sizes_and_counters(oracle, bs):
+    """Golay(24,12) decode attention in ONE pass of the tcgen05 kernel (the decode warps read the 43-codeword rows from global
+    memory, syndrome table in shared memory): every block size, ragged contexts, holes, corrected-bit / uncorrectable counters."""
+    from eccq_b200.kv_cache import paged_attention_ecc
+    Hq, Hkv, D = 8, 2, 128
+    lens = [700, 129, 5, 0, 256]
+    oc, bt = build_cache(oracle, "golay", Hkv, D, bs, lens, seed=bs + 1, ber=0.03, holes=((0, 1),))
+    q = np.random.default_rng(1).standard_normal((len(lens), Hq, D)).astype(np.float32)
+    ref, corr, det = oracle.paged_decode_attention(q, oc, bt, np.array(lens), 1)
+    assert det > 0                                  # BER 0.03: some words carry four or more flips
+    ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+    out = paged_attention_ecc(dev(q), dev(oc.k_cache), dev(oc.v_cache), dev(bt), dev(np.array(lens, np.int32)), dev(oc.k_scales), 1, bs,
+                              codec="golay", v_scales=dev(oc.v_scales), counters=ctr)
+    assert np.abs(out.cpu().numpy() - ref).max() < TOL_F32
+    assert (int(ctr[0]), int(ctr[1])) == (corr, det)
+    assert not out[3].any()
+
+
+@pytest.mark.gpu
+def test_golay_single_pass_long_contexts(oracle):
+    """Several 2 048-token splits and items per CTA, GQA group 8 (two passes over the same tiles: counted once)."""
+    from eccq_b200.kv_cache import paged_attention_ecc
+    D, bs = 128, 16
+    lens = [4300, 2049, 2048]
+    for Hq, Hkv in ((8, 2), (8, 1)):
+        oc, bt = build_cache(oracle, "golay", Hkv, D, bs, lens, seed=Hq + Hkv, ber=0.01)
+        q = np.random.default_rng(2).standard_normal((len(lens), Hq, D)).astype(np.float32)
+        ref, corr, det = oracle.paged_decode_attention(q, oc, bt, np.array(lens), 1, precision=np.float64)
+        ctr = torch.zeros(8, dtype=torch.int64, device="cuda")
+        out = paged_attention_ecc(dev(q), dev(oc.k_cache), dev(oc.v_cache), dev(bt), dev(np.array(lens, np.int32)), dev(oc.k_scales), 1, bs,
+                                  codec="golay", v_scales=dev(oc.v_scales), counters=ctr)
+        assert np.abs(out.cpu().numpy() - ref).max() < TOL_F32
+        assert (int(ctr[0]), int(ctr[1])) == (corr, det)
+
+
 _CHILD = r"""
 import sys
 sys.path.insert(0, {root!r})
