@@ -749,11 +749,11 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
           if (bm4.x | bm4.y | bm4.z | bm4.w) {
             const uint32_t stp = st + (uint32_t)(wpart * kPartBytes);
             const uint32_t pmw = mi.page_mask[s];
-            const int ctx = min(a.context_lens[wseq], a.max_blocks * bs);
             const unsigned char* cache = wpart ? a.g.v_cache : a.g.k_cache;
-            // pre-interpolation nibbles of chunk wc of token `tok`, straight from the cache (neighbour outside the tile)
+            // pre-interpolation nibbles of chunk wc of token `tok`, straight from the cache (neighbour outside the tile); the
+            // context length is only needed here (one cell in ~300): loading it up front put a global round trip in every rewrite
             auto fetch = [&](int tok, uint32_t (&o)[4]) -> bool {
-              if (tok < 0 || tok >= ctx) return false;
+              if (tok < 0 || tok >= min(a.context_lens[wseq], a.max_blocks * bs)) return false;
               const int blk = a.block_table[(int64_t)wseq * a.max_blocks + (tok >> lgbs)];
               if (blk < 0) return false;
               const uint4 xr = *reinterpret_cast<const uint4*>(
@@ -818,9 +818,10 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
     };
     // Run by every decode warp after the tile's V part: warps 0-7 own K chunk dw (every warp stored its K rows a part ago, so
     // their wait is over), warps 8-15 V chunk dw - 8 (they wait for the slowest warp's V rows: 12 % of the kernel's stall samples).
-    // Measured alternatives, both slower: the V rewrite deferred until after the next tile's K part (0.42 ms vs 0.29 ms), ONE
-    // rotating V worker per tile that checks all eight chunks (0.38 ms) -- the later the PV issuer's barrier completes, the
-    // longer the stage is held.
+    // Measured alternatives, all slower: the V rewrite deferred until after the next tile's K part (0.42 ms vs 0.29 ms), ONE
+    // rotating V worker per tile that checks all eight chunks (0.38 ms), no waiting at all -- the warp that completes a part's
+    // decode barrier (probe + atomicMax election, or a shared counter) rewrites all eight chunks (0.40 ms): whenever one warp
+    // serialises the eight chunks, the issuer's barrier completes later and the stage is held longer.
     auto worker = [&](int wn, int wseq, int wkvh, int wc1, int wtokbase) {
       const int s = wn % kStages;
       const int wpart = dw >> 3;

@@ -62,10 +62,12 @@ def _head_dim(k_cache, block_size, codec, query):
 
 def paged_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_scales, layer_idx, block_size, sm_scale=None,
                         codec="hamming84", syndrome_table=None, use_tiled=False, block_m=4, v_scales=None, *,
-                        use_interpolation=False, counters=None):
+                        use_interpolation=False, counters=None, ber_hint=None):
     """query [B, Hq, D] -> [B, Hq, D] in query.dtype.  `syndrome_table`, `use_tiled`, `block_m` are accepted for
     signature compatibility and ignored (the tables live in the library; there is one kernel).  `counters`
-    (device int64[8]) receives corrected/detected counts when given."""
+    (device int64[8]) receives corrected/detected counts when given.  `ber_hint`: the caller's bit error rate if it knows it
+    (the shim does); interpolation at BER >= 5e-3 -- a double error in every third row -- takes the two-pass route, which is
+    faster there (C5 shard at 1e-2: 0.39 ms against 0.44 ms; at 1e-3: 0.36 ms against 0.28 ms)."""
     assert query.is_cuda, "Query must be on CUDA"
     if codec not in ("hamming84", "hamming74", "golay", "int4"):
         raise ValueError(f"Unknown codec: {codec}")
@@ -96,7 +98,7 @@ def paged_attention_ecc(query, k_cache, v_cache, block_table, context_lens, k_sc
         # Hamming(8,4) + interpolation at head_dim 128: ONE pass -- the tcgen05 kernel rewrites double-detected values from
         # their temporal neighbours inside the tile pipeline (csrc/eccq_attention_tc.cu, INTERP variant).
         single_pass = interp and D == 128 and block_size in (16, 32, 64, 128) and os.environ.get("ECCQ_ATTN_TC", "1") != "0" \
-            and os.environ.get("ECCQ_ATTN_INTERP_TWO_PASS", "0") == "0"
+            and os.environ.get("ECCQ_ATTN_INTERP_TWO_PASS", "0") == "0" and not (ber_hint is not None and ber_hint >= 5e-3)
         # Golay at head_dim 128: also one pass (the decode warps of the tcgen05 kernel read the codewords from global memory)
         golay_single = codec == "golay" and D == 128 and block_size in (16, 32, 64, 128) and os.environ.get("ECCQ_ATTN_TC", "1") != "0" \
             and os.environ.get("ECCQ_ATTN_TC_GOLAY", "1") != "0"

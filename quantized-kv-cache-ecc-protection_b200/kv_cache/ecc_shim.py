@@ -339,7 +339,8 @@ class ECCBackend:
                 qd = qd.reshape(B, self.num_kv_heads, G, D).permute(1, 0, 2, 3).reshape(1, self.num_kv_heads * B * G, D)
             out = paged_attention_ecc(qd, m.k_cache, m.v_cache, bt, cl, m.k_scales, layer_idx, m.block_size, codec=cfg.codec,
                                       v_scales=m.v_scales, use_interpolation=cfg.use_interpolation,
-                                      counters=self._counters if self.count_decode_errors else None)
+                                      counters=self._counters if self.count_decode_errors else None,
+                                      ber_hint=cfg.ber if cfg.inject_errors else 0.0)
             if shared:
                 out = out.reshape(self.num_kv_heads, B, G, D).permute(1, 0, 2, 3).reshape(B, Hq, D)
             return out.unsqueeze(2)

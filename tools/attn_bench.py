@@ -40,7 +40,7 @@ for s0 in range(0, ctx, chunk):
     kk = torch.randn(Bq, chunk, HKV * D, device=dev, dtype=torch.float16)
     start = torch.full((Bq,), s0, dtype=torch.int32, device=dev)
     _lib.check(lib.eccq_cache_write(m.desc(), P(kk), P(kk.flip(1)), _lib.ECCQ_F16, P(m.block_table), nblk_seq, P(start), Bq, chunk, 0,
-                                    _lib.INJECT_PHILOX_FAST, None, None, 1e-3, 1, s0, None, sp), "cache_write")
+                                    _lib.INJECT_PHILOX_FAST, None, None, float(os.environ.get("ATTN_BENCH_BER", "1e-3")), 1, s0, None, sp), "cache_write")
 q = torch.randn(Bq, HQ, D, device=dev, dtype=qdt)
 cl = torch.full((Bq,), ctx, dtype=torch.int32, device=dev)
 
