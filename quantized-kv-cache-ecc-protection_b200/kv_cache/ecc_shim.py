@@ -30,9 +30,11 @@ from .._lib import (CTR_CORRECTED, CTR_DETECTED, CTR_FLIPPED, CTR_INTERPOLATED, 
                     device_of, load, new_counters, ptr, stream_of)
 from .attention_ecc import paged_attention_ecc, paged_prefill_attention_ecc, read_cache
 
-# Longest context served by the fused causal prefill kernel (CUDA-core dot products: every token row is decoded once per
-# block of 8 queries); beyond it the attention is GEMM-shaped and goes through the fused read + the library's flash SDPA.
+# Longest context / largest problem served by the fused causal prefill kernel (CUDA-core dot products: every token row is decoded
+# once per block of 8 queries, ~40 thread-instructions per (query, token) pair); beyond them the attention is GEMM-shaped and goes
+# through the fused read + the library's flash SDPA.  2^25 (query, token) pairs per layer call is ~1 ms on a B200.
 _PREFILL_FUSED_MAX_CTX = int(os.environ.get("ECCQ_PREFILL_FUSED_MAX_CTX", "2048"))
+_PREFILL_FUSED_MAX_PAIRS = int(os.environ.get("ECCQ_PREFILL_FUSED_MAX_PAIRS", str(1 << 25)))
 
 
 def compute_injection_seed(base_seed: int, layer_idx: int, injection_count: int) -> int:
@@ -344,7 +346,7 @@ class ECCBackend:
             if shared:
                 out = out.reshape(self.num_kv_heads, B, G, D).permute(1, 0, 2, 3).reshape(B, Hq, D)
             return out.unsqueeze(2)
-        if max(lens) <= _PREFILL_FUSED_MAX_CTX and D <= 256:
+        if max(lens) <= _PREFILL_FUSED_MAX_CTX and B * Hq * Sq * max(lens) <= _PREFILL_FUSED_MAX_PAIRS and D <= 256:
             # ECC-fused causal prefill: ONE hand-written kernel consumes the codeword pages (decode + interpolation in the K/V
             # prologue, fp32 online softmax); no K/V tensor is materialised and no library attention kernel runs
             return paged_prefill_attention_ecc(q, m.k_cache, m.v_cache, bt, cl, m.k_scales, m.v_scales, layer_idx, m.block_size,
