@@ -425,7 +425,7 @@ extern "C" int64_t eccq_attention_workspace_bytes(int nseq, int Hq, int D, int m
   if (nseq <= 0 || Hq <= 0 || D <= 0) return 0;
   int nsplit, chunk;
   attn_plan(max_context, nsplit, chunk);
-  return (int64_t)nseq * Hq * std::max(nsplit, 2) * (D + 2) * (int64_t)sizeof(float);   // the tcgen05 kernel writes two partials per split
+  return (int64_t)nseq * Hq * nsplit * (D + 2) * (int64_t)sizeof(float);
 }
 
 extern "C" int eccq_paged_decode_attention(const eccq_cache_desc* c, const void* q, void* out, int q_dtype,
@@ -448,7 +448,7 @@ extern "C" int eccq_paged_decode_attention(const eccq_cache_desc* c, const void*
   a.force_general = getenv("ECCQ_ATTN_GENERAL") != nullptr;   // debugging aid: route everything through the general kernel
   a.interp = use_interpolation && g.codec == ECCQ_CODEC_H84; a.v_use_k_scales = v_use_k_scales; a.count_errors = count_errors && counters;
   attn_plan(max_blocks * g.bs, a.nsplit, a.chunk);
-  if (workspace_bytes < (int64_t)nseq * Hq * std::max(a.nsplit, 2) * (g.D + 2) * (int64_t)sizeof(float))
+  if (workspace_bytes < (int64_t)nseq * Hq * a.nsplit * (g.D + 2) * (int64_t)sizeof(float))
     return fail(ECCQ_EINVAL, "paged_decode_attention: workspace too small (size it with max_context = max_blocks*block_size)");
   cudaStream_t st = (cudaStream_t)stream;
   int rc;

@@ -79,8 +79,8 @@ struct Misc {
   float qscale[kQBufs][kHeadsPerPass];        // 2^(e-27) * sm_scale * log2(e) per head (0 for unused heads)
   int32_t qc01[kQBufs][kHeadsPerPass];        // 8 * sum_d (d0*128 + d1)
   int32_t qc23[kQBufs][kHeadsPerPass];        // 8 * sum_d (d2*128 + d3)
-  alignas(16) float red[kSoftmaxWarps][8];           // rare-path exchange of a softmax group: max score of the 4 heads, max v scale
-  alignas(16) float fin[kSoftmaxWarps][8];           // end-of-item reduction: l and sum(w) of the 4 heads per warp
+  alignas(16) float red[2][kSoftmaxWarps][4];        // rare-path exchange of the softmax warps: max score of the 2 heads, max v scale
+  alignas(16) float fin[kSoftmaxWarps][4];           // end-of-item reduction: l and sum(w) of the 2 heads per warp
   uint32_t page_mask[kStages];           // bit j: page j of the stage's tile was loaded
   alignas(16) int32_t rowtab[2][128];                // per producer: [2 segments][32] gather rows, then [2][32] pages (scale rows)
   alignas(16) uint32_t colflag[kStages][2][8][4];    // INTERP: [stage][part][16-byte column chunk]: bit r = token row r holds a double-detected value
@@ -102,7 +102,6 @@ struct alignas(64) Args {
   float* ws;
   const float* vscales;
   int max_blocks, nseq, Hq, layer, nsplit, chunk, npass, count_errors;
-  int nslots;   // partials per (sequence, q-head) in the workspace: 2 per split (even tiles, odd tiles)
   float sm_scale;
 };
 
@@ -285,8 +284,8 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&mi.sready[b], 1);
-      mbar_init(&mi.sfree[b], kSoftmaxThreads / 2);   // one softmax group (4 warps) per buffer: tile parity
-      mbar_init(&mi.wready[b], kSoftmaxThreads / 2);
+      mbar_init(&mi.sfree[b], kSoftmaxThreads);
+      mbar_init(&mi.wready[b], kSoftmaxThreads);
       mbar_init(&mi.oready[b], 1);
     }
     for (int b = 0; b < kQBufs; ++b) mbar_init(&mi.qready[b], 4);   // one arrival per preparing warp (= per q-head of the pass)
@@ -311,7 +310,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
   tc_before();
   __syncthreads();
   tc_after();
-  const uint32_t tmem = mi.tmem_base;   // columns [0,32): two S buffers, [32,64): two O accumulators (even / odd tiles)
+  const uint32_t tmem = mi.tmem_base;   // columns [0,32): two S buffers, [32,48): the O accumulator
 
   if (warp == 0 || warp == 2) {
     // =============================================================== producers: role 0 = K codewords + K scales, role 2 = V
@@ -447,7 +446,7 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
           const uint32_t keep = mi.pv_fresh[b] ? 0u : 1u;          // accumulate onto the previous tiles' product, or start over
           const uint64_t va = vdesc0 + (uint64_t)(s * (kStageBytes >> 4)), wa = wdesc0 + (uint64_t)(b * (kWBytes >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_i8(tmem + 32 + 16 * b, va + 256 * k, wa + 32 * k, kIdescO, k > 0 ? 1u : keep);
+          for (int k = 0; k < 4; ++k) tc_mma_i8(tmem + 32, va + 256 * k, wa + 32 * k, kIdescO, k > 0 ? 1u : keep);
           tc_commit(&mi.oready[b]);
           tc_commit(&mi.empty[s]);       // every MMA that reads this stage has completed (S(n) was consumed before W(n) existed)
         }
@@ -457,21 +456,24 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
     }
   } else if (warp >= 4 && warp < 4 + kSoftmaxWarps) {
     // =============================================================== softmax / accumulate
-    // Eight warps in two groups of four.  Group g owns the tiles with (tile number & 1) == g -- S buffer g, weight buffer g, O
-    // accumulator g -- and runs its own online softmax over them for all four q-heads of the pass: two independent streams
-    // (exactly like two context splits: each writes its own partial, slot 2 * split + g, and the merge kernel combines them), so two
-    // tiles are in flight in the softmax warps and neither group ever synchronises with the other.  (Until round 2 all eight warps
-    // worked on ONE tile, two heads per group: the 124-instruction chain per tile, at ~19 cycles per instruction next to four
-    // always-ready decode warps per sub-partition, was the serial path of the kernel.)  Thread = token row of S and dim row of O
-    // inside its TMEM lane quarter.
+    // Eight warps: group g = 0/1 owns q-heads 2g, 2g+1 of the pass (S columns 8g..8g+7, the same columns of O, bytes 8g..8g+7
+    // of every weight row); thread = token row of S and dim row of O inside its TMEM lane quarter.
     const int wi = warp - 4;                              // 0..7
     const int g = wi >> 2;
     const int w = (int)(threadIdx.x >> 5) & 3;            // TMEM lane quarter = physical warp id mod 4
     const int r = w * 32 + lane;
     const uint32_t tlane = (uint32_t)(w * 32) << 16;
     const bool tracer = wi == 0 && lane == 0;
-    constexpr int kGroupThreads = kSoftmaxThreads / 2;
-    auto group_wait = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
+    // A wait that is likely to block: ONE warp of the group polls the mbarrier (each probe costs issue slots: the hinted
+    // try_wait wakes every few dozen cycles), the other three sleep in a hardware named barrier, which costs nothing.
+    auto group_wait = [&](uint64_t* bar, uint32_t parity) {
+#if ECCQ_TC_GROUPWAIT
+      if ((wi & 3) == 0) mbar_wait(bar, parity);
+      named_bar_sync(2 + g, 128);
+#else
+      mbar_wait(bar, parity);
+#endif
+    };
     // ---- query digits.  Warp wi < 4 prepares q-head wi of a pass: lane = 4 consecutive dims; the digits go to the item's
     // buffer (three buffers: item i+2 is prepared when item i is finished, so the S issuer never waits for it and the
     // buffer's previous user, item i-1, is long done).  It used to run on a producer warp, where its ~1000 instructions
@@ -550,30 +552,31 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
     };
     prep_next_q();
     prep_next_q();
-    int n0 = 0, j = 0;                     // tile number of the item's first tile, index among the non-empty items
-    int o_waited = g - 2;                  // last tile of this group whose PV completion has been seen
+    int n = 0, j = 0;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       Item it;
       const bool live = get_item(a, item, it);
       const int g0 = it.pass * kHeadsPerPass;
       const int ng = min(kHeadsPerPass, G - g0);
-      float* const ws0 = a.ws + (((int64_t)it.seq * a.Hq + it.kvh * G + g0) * a.nslots + 2 * it.split + g) * (kD + 2);   // head 0 of the pass
-      const int64_t ws_head = (int64_t)a.nslots * (kD + 2);
-      const int tfirst = (n0 ^ g) & 1;     // this group's first tile of the item
-      if (!live || tfirst >= it.ntiles) {  // empty split, or a one-tile item of the other parity: neutral partial
-        for (int hh = 0; hh < ng; ++hh) {
-          float* wsrow = ws0 + hh * ws_head;
-          wsrow[r] = 0.0f;
-          if (r == 0) { wsrow[kD] = -INFINITY; wsrow[kD + 1] = 0.0f; }
+      if (!live) {   // empty split: neutral partial
+        for (int hh = 0; hh < 2; ++hh) {
+          const int gi = 2 * g + hh;
+          if (gi < ng) {
+            float* wsrow = a.ws + (((int64_t)it.seq * a.Hq + it.kvh * G + g0 + gi) * a.nsplit + it.split) * (kD + 2);
+            wsrow[r] = 0.0f;
+            if (r == 0) { wsrow[kD] = -INFINITY; wsrow[kD + 1] = 0.0f; }
+          }
         }
-        if (live) { named_bar_sync(3, kSoftmaxThreads); n0 += it.ntiles; prep_next_q(); ++j; }
         continue;
       }
       const int qb = j % kQBufs;
       mbar_wait(&mi.qready[qb], (j / kQBufs) & 1);
-      // Running state.  The PV products of the group's tiles ACCUMULATE in TMEM (exact int32) for as long as neither the running
+      float qs[2]; int32_t c01[2], c23[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) { qs[hh] = mi.qscale[qb][2 * g + hh]; c01[hh] = mi.qc01[qb][2 * g + hh]; c23[hh] = mi.qc23[qb][2 * g + hh]; }
+      // Running state.  The PV products of consecutive tiles ACCUMULATE in TMEM (exact int32) for as long as neither the running
       // maxima nor the weight scale move -- after the first tile of an item that is almost always -- so the steady state of a
-      // tile is: read S, one barrier-with-OR ("does anyone exceed the running maximum?"), exponentials, one 16-byte store.
+      // tile is: read S, one barrier-with-OR ("does anyone exceed the running maximum?"), exponentials, one 8-byte store.
       // Lazy rescaling: the running maximum only moves when a score exceeds it by more than kSlack (base-2 units), so weights
       // may reach 2^kSlack; the 32-bit fixed-point format keeps kSlackBits of headroom for that and 28 bits below one.  (With
       // an exact running maximum every other tile of a 16-tile item set a new record for one of the four heads.)  The
@@ -583,26 +586,27 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
       constexpr float kNegBig = -1.0e30f;
       constexpr int kSlackBits = 4;
       constexpr float kSlack = (float)kSlackBits;
-      float m_run[4], l_thr[4], lw_thr[4], oacc[4];
+      float m_run[2], l_thr[2], lw_thr[2], oacc[2];
 #pragma unroll
-      for (int hh = 0; hh < 4; ++hh) { m_run[hh] = kNegBig; l_thr[hh] = 0.0f; lw_thr[hh] = 0.0f; oacc[hh] = 0.0f; }
+      for (int hh = 0; hh < 2; ++hh) { m_run[hh] = kNegBig; l_thr[hh] = 0.0f; lw_thr[hh] = 0.0f; oacc[hh] = 0.0f; }
       uint32_t eb_run = 0;                 // biased exponent bound of the v scales seen so far
       float wscale = 0.0f, sigma = 0.0f;   // 2^(24-E), 2^(E-24)
       bool o_pending = false;              // TMEM holds products not yet folded into oacc
-      auto wait_o = [&](int nn) {          // nn: a tile of this group; PVs complete in order
+      int o_waited = n - 1;                // last tile whose PV completion (oready phase) has been consumed
+      auto wait_o = [&](int nn) {          // every oready phase is consumed exactly once, in order
         if (o_waited < nn) {
-          group_wait(&mi.oready[g], (nn >> 1) & 1);
+          group_wait(&mi.oready[nn & 1], (nn >> 1) & 1);
           if (tracer) TC_TRACE(nn, EV_O_READY);
           o_waited = nn;
         }
       };
       auto drain_o = [&]() {               // TMEM accumulator (relative to m_run / sigma) -> oacc
         tc_after();
-        uint32_t o[16];
-        tmem_ld16(tmem + 32 + g * 16 + tlane, o);
+        uint32_t o[8];
+        tmem_ld8(tmem + 32 + g * 8 + tlane, o);
         tc_before();
 #pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
+        for (int hh = 0; hh < 2; ++hh) {
           float v = __int2float_rn((int32_t)o[4 * hh + 3]);
           v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * hh + 2]));
           v = fmaf(v, 256.0f, __int2float_rn((int32_t)o[4 * hh + 1]));
@@ -611,63 +615,51 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
         }
         o_pending = false;
       };
-      int nlast = -1;
-      for (int t = tfirst; t < it.ntiles; t += 2) {
-        const int n = n0 + t;              // (n & 1) == g
-        const int s = n % kStages;
+      for (int t = 0; t < it.ntiles; ++t, ++n) {
+        const int s = n % kStages, b = n & 1;
         const unsigned char* st = sm + kOffStages + (size_t)s * kStageBytes;
         mbar_wait(&mi.full[s], (n / kStages) & 1);
         const int tok = (it.tile0 + t) * kTile + r;
         const bool valid = tok < it.c1 && ((mi.page_mask[s] >> (r >> lgbs)) & 1u);
         const float ks = reinterpret_cast<const float*>(st + 2 * kPartBytes)[r];
         const float vs = valid ? reinterpret_cast<const float*>(st + 2 * kPartBytes + kTile * 4)[r] : 0.0f;
-        const float4 qs4 = *reinterpret_cast<const float4*>(&mi.qscale[qb][0]);
-        const int4 c01 = *reinterpret_cast<const int4*>(&mi.qc01[qb][0]), c23 = *reinterpret_cast<const int4*>(&mi.qc23[qb][0]);
-        const float qs[4] = {qs4.x, qs4.y, qs4.z, qs4.w};
-        const int32_t k01[4] = {c01.x, c01.y, c01.z, c01.w}, k23[4] = {c23.x, c23.y, c23.z, c23.w};
-        group_wait(&mi.sready[g], (n >> 1) & 1);
+        group_wait(&mi.sready[b], (n >> 1) & 1);
         if (tracer) TC_TRACE(n, EV_SM_START);
         tc_after();
-        uint32_t sr[16];
-        tmem_ld16(tmem + g * 16 + tlane, sr);
+        uint32_t sr[8];
+        tmem_ld8(tmem + b * 16 + g * 8 + tlane, sr);
         tc_before();
-        mbar_arrive(&mi.sfree[g]);
-        float sc[4];
+        mbar_arrive(&mi.sfree[b]);
+        float sc[2];
         bool need = (__float_as_uint(vs) >> 23) > eb_run;
 #pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
-          const int32_t hi = (int32_t)sr[4 * hh] * 128 + (int32_t)sr[4 * hh + 1] - k01[hh];
-          const int32_t lo = (int32_t)sr[4 * hh + 2] * 128 + (int32_t)sr[4 * hh + 3] - k23[hh];
+        for (int hh = 0; hh < 2; ++hh) {
+          const int32_t hi = (int32_t)sr[4 * hh] * 128 + (int32_t)sr[4 * hh + 1] - c01[hh];
+          const int32_t lo = (int32_t)sr[4 * hh + 2] * 128 + (int32_t)sr[4 * hh + 3] - c23[hh];
           const float f = fmaf(__int2float_rn(hi), 16384.0f, __int2float_rn(lo));
           sc[hh] = valid ? f * (ks * qs[hh]) : kNegBig;
           need |= sc[hh] > m_run[hh] + kSlack;
         }
-        bool fresh = t == tfirst;
-        if (named_bar_or(1 + g, kGroupThreads, need)) {
+        bool fresh = t == 0;
+        if (named_bar_or(1, kSoftmaxThreads, need)) {
           // ---- rare: a maximum or the weight scale moves (for any head: PV starts over for all 16 columns at once).  Exchange
           // the tile maxima, fold what TMEM holds into oacc under the old scales, rescale the running sums.
-          float wm[4];
-#pragma unroll
-          for (int hh = 0; hh < 4; ++hh) wm[hh] = warp_max_f32(sc[hh]);
-          const float wv = warp_max_f32(vs);
-          if (lane == 0) {
-            *reinterpret_cast<float4*>(&mi.red[wi][0]) = make_float4(wm[0], wm[1], wm[2], wm[3]);
-            mi.red[wi][4] = wv;
-          }
-          named_bar_sync(1 + g, kGroupThreads);
-          float tm[4] = {kNegBig, kNegBig, kNegBig, kNegBig}, vsmax = 0.0f;
+          const float wm0 = warp_max_f32(sc[0]), wm1 = warp_max_f32(sc[1]), wv = warp_max_f32(vs);
+          if (lane == 0) *reinterpret_cast<float4*>(&mi.red[b][wi][0]) = make_float4(wm0, wm1, wv, 0.0f);
+          named_bar_sync(1, kSoftmaxThreads);
+          float tm0 = kNegBig, tm1 = kNegBig, vsmax = 0.0f;
 #pragma unroll
           for (int ww = 0; ww < 4; ++ww) {
-            const float4 x = *reinterpret_cast<const float4*>(&mi.red[g * 4 + ww][0]);
-            tm[0] = fmaxf(tm[0], x.x); tm[1] = fmaxf(tm[1], x.y); tm[2] = fmaxf(tm[2], x.z); tm[3] = fmaxf(tm[3], x.w);
-            vsmax = fmaxf(vsmax, mi.red[g * 4 + ww][4]);
+            const float4 x = *reinterpret_cast<const float4*>(&mi.red[b][g * 4 + ww][0]);
+            tm0 = fmaxf(tm0, x.x); tm1 = fmaxf(tm1, x.y); vsmax = fmaxf(vsmax, x.z);
           }
           if (o_pending) {
-            wait_o(nlast);
+            wait_o(n - 1);
             drain_o();
           }
+          const float tm[2] = {tm0, tm1};
 #pragma unroll
-          for (int hh = 0; hh < 4; ++hh) {
+          for (int hh = 0; hh < 2; ++hh) {
             const float mn = fmaxf(m_run[hh], tm[hh]);
             const float al = exp2f(m_run[hh] - mn);     // sentinel - finite underflows to 0, sentinel - sentinel = 0 gives 1
             m_run[hh] = mn;
@@ -681,62 +673,54 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
           wscale = __uint_as_float((285u - kSlackBits - eb_run) << 23);
           sigma = __uint_as_float((eb_run - 31u + kSlackBits) << 23);
           fresh = true;
-          named_bar_sync(1 + g, kGroupThreads);   // mi.red is free for the group's next exchange
         }
-        uint32_t wfix[4];
+        uint32_t wfix[2];
 #pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
+        for (int hh = 0; hh < 2; ++hh) {
           const float p = valid ? exp2f(sc[hh] - m_run[hh]) : 0.0f;
           l_thr[hh] += p;
           wfix[hh] = __float2uint_rn(p * vs * wscale);
           // the "-8" term uses the weight the tensor core sees, so a weight's rounding error multiplies (nibble - 8), not the nibble
           lw_thr[hh] = fmaf(__uint2float_rn(wfix[hh]), sigma, lw_thr[hh]);
         }
-        if (nlast >= 0) wait_o(nlast);     // PV of the group's previous tile has read this weight buffer (long complete by now)
-        *reinterpret_cast<uint4*>(sm + kOffW + g * kWBytes + r * 16) = make_uint4(wfix[0], wfix[1], wfix[2], wfix[3]);
-        if (r == 0) mi.pv_fresh[g] = fresh ? 1u : 0u;
+        *reinterpret_cast<uint2*>(sm + kOffW + b * kWBytes + r * 16 + g * 8) = make_uint2(wfix[0], wfix[1]);
+        if (r == 0 && g == 0) mi.pv_fresh[b] = fresh ? 1u : 0u;
         fence_async_smem();
-        mbar_arrive(&mi.wready[g]);
+        mbar_arrive(&mi.wready[b]);
         if (tracer) TC_TRACE(n, EV_SM_W);
         o_pending = true;
-        nlast = n;
+        if (t > 0) wait_o(n - 1);          // long complete by now; keeps the barrier phases in step
       }
-      wait_o(nlast);
+      wait_o(n - 1);
       drain_o();
-      if (tracer) TC_TRACE(nlast, EV_O_DONE);
-      // ---- end of item: sums over the 128 token threads of the group, write the group's partial
+      if (tracer) TC_TRACE(n - 1, EV_O_DONE);
+      // ---- end of item: sums over the 128 token threads of the group, write the partial
 #pragma unroll
-      for (int hh = 0; hh < 4; ++hh)
+      for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           l_thr[hh] += __shfl_xor_sync(0xFFFFFFFFu, l_thr[hh], o);
           lw_thr[hh] += __shfl_xor_sync(0xFFFFFFFFu, lw_thr[hh], o);
         }
-      if (lane == 0) {
-        *reinterpret_cast<float4*>(&mi.fin[wi][0]) = make_float4(l_thr[0], l_thr[1], l_thr[2], l_thr[3]);
-        *reinterpret_cast<float4*>(&mi.fin[wi][4]) = make_float4(lw_thr[0], lw_thr[1], lw_thr[2], lw_thr[3]);
-      }
-      named_bar_sync(1 + g, kGroupThreads);
-      float L[4] = {0, 0, 0, 0}, LW[4] = {0, 0, 0, 0};
+      if (lane == 0) *reinterpret_cast<float4*>(&mi.fin[wi][0]) = make_float4(l_thr[0], l_thr[1], lw_thr[0], lw_thr[1]);
+      named_bar_sync(1, kSoftmaxThreads);
+      float L[2] = {0, 0}, LW[2] = {0, 0};
 #pragma unroll
       for (int ww = 0; ww < 4; ++ww) {
-        const float4 x = *reinterpret_cast<const float4*>(&mi.fin[g * 4 + ww][0]), y = *reinterpret_cast<const float4*>(&mi.fin[g * 4 + ww][4]);
-        L[0] += x.x; L[1] += x.y; L[2] += x.z; L[3] += x.w; LW[0] += y.x; LW[1] += y.y; LW[2] += y.z; LW[3] += y.w;
+        const float4 x = *reinterpret_cast<const float4*>(&mi.fin[g * 4 + ww][0]);
+        L[0] += x.x; L[1] += x.y; LW[0] += x.z; LW[1] += x.w;
       }
 #pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
-        if (hh < ng) {
-          float* wsrow = ws0 + hh * ws_head;
+      for (int hh = 0; hh < 2; ++hh) {
+        const int gi = 2 * g + hh;
+        if (gi < ng) {
+          float* wsrow = a.ws + (((int64_t)it.seq * a.Hq + it.kvh * G + g0 + gi) * a.nsplit + it.split) * (kD + 2);
           wsrow[r] = fmaf(-8.0f, LW[hh], oacc[hh]);
           // the merge kernel works in natural-log units
           if (r == 0) { wsrow[kD] = (m_run[hh] <= kNegBig) ? -INFINITY : m_run[hh] * 0.6931471805599453f; wsrow[kD + 1] = L[hh]; }
         }
       }
-      named_bar_sync(1 + g, kGroupThreads);        // mi.fin is reused by the group's next item
-      // The two groups meet once per item: the query buffers and their barriers are shared and three deep, so neither group may
-      // run a whole item ahead of the other (the groups alternate tiles and finish within about a tile of each other).
-      named_bar_sync(3, kSoftmaxThreads);
-      n0 += it.ntiles;
+      named_bar_sync(1, kSoftmaxThreads);          // mi.fin is reused by the next item; every S of this item has been consumed
       prep_next_q();                               // item j + 2 into the buffer item j - 1 used
       ++j;
     }
@@ -1093,17 +1077,14 @@ int try_attn_tc(const CacheGeom& g, AttnArgs& a, int q_dtype, uint64_t* counters
   t.max_blocks = a.max_blocks; t.nseq = a.nseq; t.Hq = a.Hq; t.layer = a.layer; t.sm_scale = a.sm_scale;
   t.npass = (G + tc::kHeadsPerPass - 1) / tc::kHeadsPerPass;
   t.count_errors = a.count_errors;
-  // splits: multiples of the 128-token tile, at least 2048 tokens; every split writes TWO partials (even / odd tiles, one per
-  // softmax group), and there are never more partials than the workspace was planned for (max(planned splits, 2) slots)
+  // splits: multiples of the 128-token tile, at least 2048 tokens, never more splits than the workspace was planned for
   const int64_t maxctx = (int64_t)a.max_blocks * g.bs;
-  const int max_splits = std::max(1, std::max(a.nsplit, 2) / 2);
-  int chunk = (int)(((maxctx + max_splits - 1) / max_splits + tc::kTile - 1) / tc::kTile * tc::kTile);
+  int chunk = (int)(((maxctx + a.nsplit - 1) / a.nsplit + tc::kTile - 1) / tc::kTile * tc::kTile);
   static const int min_chunk = [] { const char* v = std::getenv("ECCQ_ATTN_TC_CHUNK"); return v && *v ? std::atoi(v) : 2048; }();
   chunk = std::max(chunk, std::max(min_chunk / tc::kTile * tc::kTile, tc::kTile));
   a.chunk = chunk;
-  t.nsplit = (int)((maxctx + chunk - 1) / chunk);
-  t.chunk = a.chunk; t.nslots = 2 * t.nsplit;
-  a.nsplit = t.nslots;             // what the merge kernel combines
+  a.nsplit = (int)((maxctx + chunk - 1) / chunk);
+  t.chunk = a.chunk; t.nsplit = a.nsplit;
   static const int ndec = [] { const char* v = std::getenv("ECCQ_ATTN_TC_NDEC"); return v && *v ? std::atoi(v) : 16; }();
   int rc;
 #define ECCQ_TC_CASE(C, CNT)                                            \
