@@ -32,7 +32,7 @@
 // 4 096-entry syndrome table held in shared memory and writes the nibbles into the tile at the swizzled byte positions.
 //
 // Temporal interpolation of double-detected values (ECCShimConfig.use_interpolation, kv_cache/ecc_shim.py:1038-1059 +
-// interpolation_triton.py:120-159) runs in the SAME pass (template parameter INTERP): the decode warps leave bit 7 set on every
+// interpolation_triton.py:120-159) runs in the SAME pass (template parameter INTERP): the decode warps leave bit 6 set on every
 // double-detected byte and set bit (row) of their 16-byte column chunk's bitmap.  Interpolation runs along the token axis at a
 // fixed dim, so the eight column chunks of a part are independent: once every row of the part is stored (the part's decode
 // barrier), decode warp w < 8 rewrites the flagged cells of K chunk w, warp 8 + w those of V chunk w -- (left + right + 1) >> 1
@@ -250,6 +250,11 @@ __device__ __forceinline__ uint32_t decode_nibbles(uint32_t w, FlagCount& fc, bo
 
 // swizzled byte offset of 16-byte chunk c of token row r inside a K or V tile (128-byte swizzle, K-major / MN-major alike)
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+// INTERP: flip table with the double-error mark (see the decode warps): entries of the non-zero syndromes carry bit 7
+constexpr uint32_t kFlipMarkLutLo = kFlipLutLo | 0x80808000u, kFlipMarkLutHi = kFlipLutHi | 0x80808080u;
+constexpr uint32_t kMarkBits = 0x40404040u;
+// pre-interpolation nibbles of four bytes of a decoded INTERP tile: a marked byte (bit 6) holds its nibble inverted
+__device__ __forceinline__ uint32_t mark_nib(uint32_t w) { return (w ^ (((w >> 6) & M01) * 0x0Fu)) & M0F; }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 x;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(addr));
@@ -785,27 +790,27 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
                   upok = row_ok(r - 1);
                 } else {
                   const uint4 u = lds128(stp + swz(r - 1, wc));
-                  up[0] = u.x & M0F; up[1] = u.y & M0F; up[2] = u.z & M0F; up[3] = u.w & M0F;
+                  up[0] = mark_nib(u.x); up[1] = mark_nib(u.y); up[2] = mark_nib(u.z); up[3] = mark_nib(u.w);
                   upok = row_ok(r - 1);
                 }
                 if (r == kTile - 1) {
                   dnok = fetch(wtokbase + kTile, dn);
                 } else {
                   const uint4 d = lds128(stp + swz(r + 1, wc));
-                  dn[0] = d.x & M0F; dn[1] = d.y & M0F; dn[2] = d.z & M0F; dn[3] = d.w & M0F;
+                  dn[0] = mark_nib(d.x); dn[1] = mark_nib(d.y); dn[2] = mark_nib(d.z); dn[3] = mark_nib(d.w);
                   dnok = row_ok(r + 1);
                 }
               }
               __syncwarp();   // every read of the group precedes its writes
               carry_set = (bmq >> 31) & 1u;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) carry[k] = __shfl_sync(0xFFFFFFFFu, sw[k] & M0F, 31);
+              for (int k = 0; k < 4; ++k) carry[k] = __shfl_sync(0xFFFFFFFFu, mark_nib(sw[k]), 31);
               if (mine) {
                 uint32_t nw[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  const uint32_t sn4 = sw[k] & M0F;
-                  nw[k] = interp4(sn4, upok ? up[k] : sn4, dnok ? dn[k] : sn4, (sw[k] >> 7) & M01);   // a missing neighbour = the value itself
+                  const uint32_t sn4 = mark_nib(sw[k]);
+                  nw[k] = interp4(sn4, upok ? up[k] : sn4, dnok ? dn[k] : sn4, (sw[k] >> 6) & M01);   // a missing neighbour = the value itself
                 }
                 sts128(stp + swz(r, wc), make_uint4(nw[0], nw[1], nw[2], nw[3]));
               }
@@ -948,20 +953,24 @@ __global__ void __launch_bounds__((kFrontWarps + NDEC) * 32, 1) attn_tc_kernel(c
             }
             uint32_t y0, y1, y2, y3;
             if constexpr (INTERP) {
-              // double-detected bytes keep bit 7 set (flag byte 0xFF: only doubles have bit 0) and raise their row's flag; the
-              // issuer warp of the part rewrites those rows before the MMAs read them
+              // ONE look-up serves the correction and the double-error mark: the flip table with bit 7 set on every entry of a
+              // non-zero syndrome.  Parity mismatch (single error): the entry is read as it is, flip bit | 0x80; parity match (PRMT
+              // sign-replicate mode): 0x00 for syndrome 0, 0xFF for a non-zero syndrome = double error.  (x & 0x0F) ^ (v & 0x4F)
+              // then corrects a single error, and for a double error leaves bit 6 set on the byte with its nibble INVERTED (the
+              // byte is rewritten by the interpolation anyway; mark_nib() undoes the inversion where the old value is needed).
+              // Two LOP3 + the OR below per word on top of the plain decode (the first version spent a second PRMT, a shift and
+              // two LOP3 on a separate flag byte).
               const uint32_t w4[4] = {x[part][i].x, x[part][i].y, x[part][i].z, x[part][i].w};
               uint32_t y4[4], any = 0;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                uint32_t fl;
-                hamming_decode4<ECCQ_CODEC_H84>(w4[k], y4[k], fl);
-                if (COUNT) fc.add(cnt ? fl : 0u);
-                const uint32_t mk = (fl << 7) & 0x80808080u;
-                y4[k] |= mk;
-                any |= mk;
+                const uint32_t sel = hamming_sel4<ECCQ_CODEC_H84>(w4[k]);
+                if (COUNT) fc.add(cnt ? prmt(kFlagLutLo, kFlagLutHi, sel) : 0u);
+                const uint32_t v = prmt(kFlipMarkLutLo, kFlipMarkLutHi, sel);
+                y4[k] = lop3<kLopXorAnd>(w4[k] & M0F, v, 0x4F4F4F4Fu);
+                any |= y4[k];
               }
-              if (any) {
+              if (any & kMarkBits) {
                 const int row = (dw + i * NDEC) * 4 + (lane >> 3);
                 atomicOr(&mi.colflag[s][part][lane & 7][row >> 5], 1u << (row & 31));
               }
