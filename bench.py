@@ -283,7 +283,8 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    affinity = bind_to_gpu_numa_node(local)      # before the pinned host buffers are allocated (first touch decides the node)
+    # before the pinned host buffers are allocated (first touch decides the node); ECCQ_BENCH_NUMA=0 leaves the placement to the OS
+    affinity = bind_to_gpu_numa_node(local) if os.environ.get("ECCQ_BENCH_NUMA", "1") != "0" else {"disabled": True}
     lib = _lib.load()
     # weak scaling: every rank owns a full C3 batch (its own sequences and block pool); strong: the 16 sequences are split
     b_local = B if args.scaling == "weak" else max(1, B // world)
