@@ -398,6 +398,37 @@ def run_ours(args):
         ms = e0.elapsed_time(e1) / 10
         ber_sweep[f"{ber:g}"] = {"ms": ms, "gbs": BYTES_WRITE * scale / (ms * 1e-3) / 1e9, "frac": BYTES_WRITE * scale / (ms * 1e-3) / 1e9 / peak}
 
+    # ---------------- validation of what the timed steps produced (outside the timed region).  The own-stream injector is only
+    # statistically specified, so the step output is checked through what it must satisfy: (1) the flip counter of ONE more write
+    # against BER x candidate bits (relative sigma 2e-4 at this size: 1 % is > 40 sigma); (2) decode counters of ONE more read of
+    # that image against the Hamming(8,4) rates of i.i.d. flips (single: 7 p (1-p)^7 per codeword, double: 28 p^2 (1-p)^6);
+    # (3) the dequantised read of one sequence against its fp16 input: every value within half a quantisation step of the input
+    # unless its codeword took an uncorrectable hit (>= 3 flips, or 2 with both neighbours' interpolation off by more) -- the
+    # fraction outside must stay below the >= 2-flip rate.
+    validation = None
+    try:
+        cv = _lib.new_counters(dev)
+        _lib.check(lib.eccq_cache_write(descs[0], P(k), P(v), _lib.ECCQ_F16, P(images[0].block_table), nblk_seq, None, b_local, S, 0,
+                                        _lib.INJECT_PHILOX_FAST, None, None, BER, SEED, 12345, P(cv), sp), "cache_write")
+        _lib.check(lib.eccq_cache_read(descs[0], P(images[0].block_table), nblk_seq, P(cl), b_local, S, 0, 1, _lib.ECCQ_F16, P(k_out), P(v_out),
+                                       None, None, P(cv), sp), "cache_read")
+        torch.cuda.synchronize(dev)
+        c = cv.tolist()
+        ncw = 2 * b_local * S * HKV * D                       # codewords written (K and V)
+        flip_rate = c[2] / (8.0 * ncw)
+        p1 = 7 * BER * (1 - BER) ** 7                          # a lone flip of the overall-parity bit is not counted
+        p2 = 28 * BER ** 2 * (1 - BER) ** 6
+        kin = k[0].float().view(S, HKV, D)
+        sc = kin.abs().amax(dim=-1, keepdim=True) / 7.0
+        bad = ((k_out[0].float() - kin).abs() > 0.505 * sc).float().mean().item()   # half a step + the fp16 rounding of the output
+        validation = {"flip_rate": flip_rate, "expected_ber": BER, "corrected_per_codeword": c[0] / ncw, "expected_single": p1,
+                      "detected_per_codeword": c[1] / ncw, "expected_double": p2, "values_off_by_more_than_half_a_step": bad,
+                      "bound_two_or_more_flips": 1 - (1 - BER) ** 8 - 8 * BER * (1 - BER) ** 7}
+        validation["ok"] = bool(abs(flip_rate / BER - 1) < 0.01 and abs(c[0] / ncw / p1 - 1) < 0.02 and abs(c[1] / ncw / p2 - 1) < 0.05
+                                and bad < validation["bound_two_or_more_flips"])
+    except Exception as exc:
+        validation = {"error": repr(exc)}
+
     # ---------------- statistics: the only collective of the path (NCCL all-reduce of the counter vector)
     stats = all_reduce_counters(counters).tolist()
 
@@ -519,7 +550,7 @@ def run_ours(args):
                            "l2": "inputs 537 MB >> 126 MB L2; read consumes the cache image written one step earlier (ping-pong)",
                            "algorithmic_bytes_per_step": BYTES_STEP * scale},
                 "roofline": roofline, "kernels": kern, "write_kernel_ber_sweep": ber_sweep, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": 2 * K,
-                "clocks": sampler.report(),
+                "clocks": sampler.report(), "validation": validation,
                 "counters": {"corrected": stats[0], "detected": stats[1], "bits_flipped": stats[2], "interpolated": stats[5]},
                 "c1": c1, "decode_attention": attn, "golay_c4": golay, "reference_triton": ref_triton}
         print(json.dumps(line), flush=True)
