@@ -156,6 +156,10 @@ def test_single_pass_interpolation(oracle, bs, ber):
     out2 = paged_attention_ecc(dev(q), dev(oc.k_cache), dev(oc.v_cache), dev(bt), dev(np.array(lens, np.int32)), dev(oc.k_scales), 1, bs,
                                codec="hamming84", v_scales=dev(oc.v_scales), use_interpolation=True)      # variant without counters
     assert torch.equal(out, out2)
+    # a caller that knows its BER is >= 5e-3 is routed to the two-pass path (faster there): same corrected nibbles, same result
+    out3 = paged_attention_ecc(dev(q), dev(oc.k_cache), dev(oc.v_cache), dev(bt), dev(np.array(lens, np.int32)), dev(oc.k_scales), 1, bs,
+                               codec="hamming84", v_scales=dev(oc.v_scales), use_interpolation=True, ber_hint=ber)
+    assert np.abs(out3.cpu().numpy() - ref).max() < TOL_F32
 
 
 @pytest.mark.gpu
