@@ -380,6 +380,297 @@ static int run_attn(const CacheGeom& g, const AttnArgs& a_in, uint64_t* counters
   return ECCQ_OK;
 }
 
+// ---- ECC-fused causal prefill, tiled (head_dim 32 / 64 / 128): the kernel ECCBackend.attend uses for q_len > 1 -----------------------
+// Replaces gather + decode + interpolation + fp32 K/V materialisation + repeat_interleave + SDPA (kv_cache/ecc_shim.py:979-1089,
+// :1138-1164).  CTA = 32 query rows of ONE kv-head (row = (query position, q-head of the GQA group): the group shares every decoded
+// K/V row), 8 warps x 4 rows.  Per 32-token tile: (1) the warps decode 4 token rows each straight from the codeword pages -- the
+// row prologue of attn_partial_kernel (all codecs, temporal interpolation, counters) -- into shared memory as nibbles, one byte per
+// value, rows padded to D + 4 bytes; (2) QK^T with lane = token: the lane walks ITS row's nibbles (conflict-free through the
+// padding), the query values are 16-byte shared-memory broadcasts, fp32 FMAs, no shuffles; (3) online softmax per query row in base
+// 2, one max / sum reduction over the lanes per row and tile; (4) PV with lane = dims: the weights go through shared memory, every
+// lane accumulates its D/32 dims.  ~13 warp-instructions per (query, token) pair against ~77 for the warp-per-token kernel above.
+constexpr int kPfRows = 32;                        // query rows per CTA
+constexpr int kPfRPW = kPfRows / kAttnWarps;       // query rows per warp
+constexpr int kPfTile = 32;                        // tokens per tile (= lanes)
+template <typename TQ, int CODEC, int DPL>
+__global__ void __launch_bounds__(kAttnThreads) attn_prefill_tile_kernel(CacheGeom g, AttnArgs a, uint64_t* counters) {
+  constexpr bool GOLAY = CODEC == ECCQ_CODEC_GOLAY;
+  constexpr int D = 32 * DPL;
+  constexpr int KS = D + 4;                        // padded row stride (bytes) of the nibble tiles
+  constexpr int CW = (D + 2) / 3;                  // Golay codewords per row
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* p = smem_raw;
+  uint16_t* s_lo = nullptr; uint16_t* s_hi = nullptr; int32_t* s_syn = nullptr;
+  if (GOLAY) {
+    s_syn = reinterpret_cast<int32_t*>(p); p += 4096 * 4;
+    s_lo = reinterpret_cast<uint16_t*>(p); p += 128;
+    s_hi = reinterpret_cast<uint16_t*>(p); p += 128;
+    golay_load_parity(s_lo, s_hi);
+    golay_load_syndrome(s_syn);
+  }
+  float* Qs = reinterpret_cast<float*>(p); p += kPfRows * D * 4;                 // [row][D], pre-multiplied by sm_scale * log2(e)
+  float* Ps = reinterpret_cast<float*>(p); p += kAttnWarps * kPfRPW * kPfTile * 4;   // [warp][row][token]: weights x v scale
+  float* s_ks = reinterpret_cast<float*>(p); p += kPfTile * 4;
+  float* s_vs = reinterpret_cast<float*>(p); p += kPfTile * 4;
+  uint8_t* Kn = p; p += kPfTile * KS;                                            // nibbles of the tile's K rows
+  uint8_t* Vn = p;
+
+  const int G = a.Hq / g.H;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int i = a.nseq == 1 ? 0 : b;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ctx = min(a.context_lens[i], a.max_blocks * g.bs);
+  const int qstart = ctx - a.Sq;                   // query t sits at position qstart + t
+  const int row0 = blockIdx.x * kPfRows;           // first (position, head) row of this CTA inside the kv-head: row = pos * G + head
+  const int nrows = a.Sq * G;
+  const int pos_last = min(a.Sq - 1, (row0 + kPfRows - 1) / G);
+  const int tmax = max(0, min(ctx, qstart + pos_last + 1));   // tokens [0, tmax) are visible to some query of the CTA
+  const int32_t* bt = a.block_table + (int64_t)i * a.max_blocks;
+  const int rowbytes = GOLAY ? g.cw * 4 : D;
+  const int64_t page_bytes = (int64_t)g.bs * rowbytes;
+  const bool do_count = a.count_errors && (int)blockIdx.x == (int)gridDim.x - 1 && (a.nseq > 1 || b == 0);
+  uint32_t ncorr = 0, ndet = 0;
+
+  // ---- queries of the CTA -> shared memory
+  for (int e = threadIdx.x; e < kPfRows * D; e += kAttnThreads) {
+    const int r = e / D, d = e - r * D;
+    const int rg = row0 + r;
+    float v = 0.0f;
+    if (rg < nrows) {
+      const int pos = rg / G, hq = h * G + (rg - pos * G);
+      v = ldq<TQ>(a.q, (((int64_t)b * a.Hq + hq) * a.Sq + pos) * D + d) * (a.sm_scale * 1.4426950408889634f);
+    }
+    Qs[e] = v;
+  }
+  // this warp's query rows: position of each (for the causal mask), running state; lane = dims lane*DPL .. +DPL-1 for the output
+  int qpos[kPfRPW];
+  float m[kPfRPW], l[kPfRPW], acc[kPfRPW][DPL];
+#pragma unroll
+  for (int q = 0; q < kPfRPW; ++q) {
+    const int rg = row0 + warp * kPfRPW + q;
+    qpos[q] = rg < nrows ? qstart + rg / G : -1;   // -1: no such row, sees nothing
+    m[q] = -INFINITY; l[q] = 0.0f;
+#pragma unroll
+    for (int x = 0; x < DPL; ++x) acc[q][x] = 0.0f;
+  }
+
+  // nibble word (4 values) of a neighbour token's K or V row for the interpolation of a double-detected value (rare)
+  auto neighbour_word = [&](const uint8_t* cache, int tok, int w) -> uint32_t {
+    const int lb = tok / g.bs, slot = tok - lb * g.bs;
+    const int blk = bt[lb];
+    if (blk < 0) return 0u;
+    const uint8_t* row = cache + page_index(g, blk, a.layer, h) * page_bytes + (int64_t)slot * rowbytes;
+    return h84_decode4(__ldg(reinterpret_cast<const uint32_t*>(row) + w)).nib;
+  };
+
+  // The codeword words of the tile's rows this warp decodes (4 rows x K, V) and their scales are loaded one tile AHEAD, while the
+  // current tile is being multiplied: block table -> row -> words is a chain of dependent global loads, and a CTA walks its tiles
+  // serially, so without the prefetch every tile paid that round trip (0.73 -> 0.26 ms came from the tiling, the rest from this).
+  constexpr int RR = kPfTile / kAttnWarps;         // token rows per warp and tile
+  constexpr int NW = GOLAY ? (CW + 31) / 32 : 1;   // words per lane, row and tensor
+  struct TileRaw { uint32_t k[RR][NW], v[RR][NW]; float ks[RR], vs[RR]; int blk[RR]; };
+  auto load_tile = [&](int tile0, TileRaw& r) {
+#pragma unroll
+    for (int rr = 0; rr < RR; ++rr) {
+      const int tok = tile0 + warp * RR + rr;
+      r.blk[rr] = -1; r.ks[rr] = 0.0f; r.vs[rr] = 0.0f;
+#pragma unroll
+      for (int x = 0; x < NW; ++x) { r.k[rr][x] = 0u; r.v[rr][x] = 0u; }
+      if (tok < tmax) {
+        const int lb = tok / g.bs, slot = tok - lb * g.bs;
+        const int blk = bt[lb];
+        r.blk[rr] = blk;
+        if (blk >= 0) {
+          const int64_t pg = page_index(g, blk, a.layer, h);
+          const int64_t off = pg * page_bytes + (int64_t)slot * rowbytes;
+          r.ks[rr] = __ldg(g.k_scales + pg * g.bs + slot);
+          r.vs[rr] = a.v_use_k_scales ? r.ks[rr] : __ldg(g.v_scales + pg * g.bs + slot);
+#pragma unroll
+          for (int x = 0; x < NW; ++x) {
+            const int w = x * 32 + lane;
+            if (GOLAY ? w < CW : w < D / 4) {
+              r.k[rr][x] = __ldg(reinterpret_cast<const uint32_t*>(g.k_cache + off) + w);
+              r.v[rr][x] = __ldg(reinterpret_cast<const uint32_t*>(g.v_cache + off) + w);
+            }
+          }
+        }
+      }
+    }
+  };
+  TileRaw cur;
+  if (tmax > 0) load_tile(0, cur);
+  for (int tile0 = 0; tile0 < tmax; tile0 += kPfTile) {
+    __syncthreads();                               // the previous tile has been consumed (and Qs is written, first time round)
+    // ---- (1) decode: warp w owns token rows 4w .. 4w+3 of the tile
+#pragma unroll
+    for (int rr = 0; rr < RR; ++rr) {
+      const int trow = warp * RR + rr;
+      const int tok = tile0 + trow;
+      uint8_t* kdst = Kn + trow * KS;
+      uint8_t* vdst = Vn + trow * KS;
+      if (cur.blk[rr] < 0) {                       // past the visible range or unmapped: the token takes no part
+        if (lane == 0) { s_ks[trow] = 0.0f; s_vs[trow] = -1.0f; }   // v scale < 0 marks the row invalid
+        for (int w = lane; w < D / 4; w += 32) { reinterpret_cast<uint32_t*>(kdst)[w] = 0x08080808u; reinterpret_cast<uint32_t*>(vdst)[w] = 0x08080808u; }
+        continue;
+      }
+      if (lane == 0) { s_ks[trow] = cur.ks[rr]; s_vs[trow] = cur.vs[rr]; }
+      if (GOLAY) {
+#pragma unroll
+        for (int x = 0; x < NW; ++x) {
+          const int j = x * 32 + lane;
+          if (j < CW) {
+#pragma unroll
+            for (int kv = 0; kv < 2; ++kv) {
+              uint32_t cnt;
+              const uint32_t d = golay_decode1(s_lo, s_hi, s_syn, kv ? cur.v[rr][x] : cur.k[rr][x], cnt);
+              if (do_count) { if (cnt == 4u) ++ndet; else ncorr += cnt; }
+              uint8_t* dst = kv ? vdst : kdst;
+#pragma unroll
+              for (int v = 0; v < 3; ++v)
+                if (3 * j + v < D) dst[3 * j + v] = (uint8_t)((d >> (4 * v)) & 0xFu);
+            }
+          }
+        }
+      } else {
+        const int w = lane;
+        if (w < D / 4) {
+#pragma unroll
+          for (int kv = 0; kv < 2; ++kv) {
+            const uint8_t* cache = kv ? g.v_cache : g.k_cache;
+            const uint32_t cwv = kv ? cur.v[rr][0] : cur.k[rr][0];
+            uint32_t nib = cwv, dbl = 0;
+            if (CODEC == ECCQ_CODEC_H84) {
+              const Dec4 d = h84_decode4(cwv);
+              nib = d.nib; dbl = h84_double4(d);
+              if (do_count) { ncorr += __popc(h84_single4(d)); ndet += __popc(dbl); }
+              if (a.interp && dbl) {
+                const uint32_t left = tok > 0 ? neighbour_word(cache, tok - 1, w) : nib;
+                const uint32_t right = tok + 1 < ctx ? neighbour_word(cache, tok + 1, w) : nib;
+                nib = interp4(nib, left, right, dbl);
+              }
+            } else if (CODEC == ECCQ_CODEC_H74) {
+              const Dec4 d = h74_decode4(cwv);
+              nib = d.nib;
+              if (do_count) ncorr += __popc(d.nz);
+            }
+            reinterpret_cast<uint32_t*>(kv ? vdst : kdst)[w] = nib & 0x0F0F0F0Fu;
+          }
+        }
+      }
+    }
+    if (tile0 + kPfTile < tmax) load_tile(tile0 + kPfTile, cur);   // in flight during the products below
+    __syncthreads();
+    // ---- (2) QK^T, lane = token of the tile
+    const int tok = tile0 + lane;
+    const float ksc = s_ks[lane], vsc = s_vs[lane];
+    const bool tvalid = vsc >= 0.0f;
+    float sc[kPfRPW];
+#pragma unroll
+    for (int q = 0; q < kPfRPW; ++q) sc[q] = 0.0f;
+    const uint32_t* krow = reinterpret_cast<const uint32_t*>(Kn + lane * KS);
+#pragma unroll 4
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      const uint32_t kw = krow[d4];
+      const float k0 = byte_to_float_m8(kw, 0), k1 = byte_to_float_m8(kw, 1), k2 = byte_to_float_m8(kw, 2), k3 = byte_to_float_m8(kw, 3);
+#pragma unroll
+      for (int q = 0; q < kPfRPW; ++q) {
+        const float4 qv = *reinterpret_cast<const float4*>(Qs + (warp * kPfRPW + q) * D + d4 * 4);
+        sc[q] = fmaf(qv.x, k0, fmaf(qv.y, k1, fmaf(qv.z, k2, fmaf(qv.w, k3, sc[q]))));
+      }
+    }
+    // ---- (3) online softmax per query row (base 2), weights x v scale -> shared memory
+#pragma unroll
+    for (int q = 0; q < kPfRPW; ++q) {
+      const bool vis = tvalid && tok <= qpos[q];
+      const float sv = vis ? sc[q] * ksc : -INFINITY;
+      float mt = sv;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xFFFFFFFFu, mt, o));
+      const float mn = fmaxf(m[q], mt);
+      float pw = 0.0f, alpha = 1.0f;
+      if (mn > -INFINITY) {                        // warp-uniform
+        alpha = exp2f(m[q] - mn);                  // exp2(-inf) = 0 on the row's first visible tile
+        pw = vis ? exp2f(sv - mn) : 0.0f;
+        m[q] = mn;
+      }
+      l[q] = l[q] * alpha + warp_sum(pw);
+#pragma unroll
+      for (int x = 0; x < DPL; ++x) acc[q][x] *= alpha;
+      Ps[(warp * kPfRPW + q) * kPfTile + lane] = tvalid ? pw * vsc : 0.0f;
+    }
+    __syncwarp();
+    // ---- (4) PV, lane = dims lane*DPL .. lane*DPL+DPL-1
+#pragma unroll 2
+    for (int t4 = 0; t4 < kPfTile / 4; ++t4) {
+      float4 pv[kPfRPW];
+#pragma unroll
+      for (int q = 0; q < kPfRPW; ++q) pv[q] = *reinterpret_cast<const float4*>(Ps + (warp * kPfRPW + q) * kPfTile + t4 * 4);
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt) {
+        const uint8_t* vrow = Vn + (t4 * 4 + tt) * KS + lane * DPL;
+        uint32_t vw;
+        if (DPL == 4) vw = *reinterpret_cast<const uint32_t*>(vrow);
+        else if (DPL == 2) vw = *reinterpret_cast<const uint16_t*>(vrow);
+        else vw = *vrow;
+        float vf[DPL];
+#pragma unroll
+        for (int x = 0; x < DPL; ++x) vf[x] = byte_to_float_m8(vw, x);
+#pragma unroll
+        for (int q = 0; q < kPfRPW; ++q) {
+          const float pq = tt == 0 ? pv[q].x : tt == 1 ? pv[q].y : tt == 2 ? pv[q].z : pv[q].w;
+#pragma unroll
+          for (int x = 0; x < DPL; ++x) acc[q][x] = fmaf(pq, vf[x], acc[q][x]);
+        }
+      }
+    }
+    __syncwarp();                                  // Ps of this warp is rewritten by the next tile
+  }
+  // ---- output rows of this warp: out[b, hq, pos, lane*DPL ..]
+#pragma unroll
+  for (int q = 0; q < kPfRPW; ++q) {
+    const int rg = row0 + warp * kPfRPW + q;
+    if (rg >= nrows) continue;
+    const int pos = rg / G, hq = h * G + (rg - pos * G);
+    TQ* orow = reinterpret_cast<TQ*>(a.out) + (((int64_t)b * a.Hq + hq) * a.Sq + pos) * D + lane * DPL;
+    const float inv = l[q] > 0.0f ? 1.0f / l[q] : 0.0f;   // no visible token: zeros
+#pragma unroll
+    for (int x = 0; x < DPL; ++x) orow[x] = Cvt<TQ>::to(acc[q][x] * inv);
+  }
+  if (a.count_errors) {
+    const int idx[3] = {ECCQ_CTR_CORRECTED, ECCQ_CTR_DETECTED, ECCQ_CTR_INTERPOLATED};
+    const uint32_t val[3] = {ncorr, ndet, a.interp ? ndet : 0u};
+    block_accumulate<3>(counters, idx, val);
+  }
+}
+
+template <typename TQ, int CODEC, int DPL>
+static int launch_prefill_tile(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  constexpr int D = 32 * DPL;
+  const size_t smem = (CODEC == ECCQ_CODEC_GOLAY ? 4096 * 4 + 256 : 0) + (size_t)kPfRows * D * 4 + kAttnWarps * kPfRPW * kPfTile * 4 + 2 * kPfTile * 4 +
+                      2 * kPfTile * (D + 4);
+  auto kern = attn_prefill_tile_kernel<TQ, CODEC, DPL>;
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
+  }
+  const int G = a.Hq / g.H;
+  dim3 grid((a.Sq * G + kPfRows - 1) / kPfRows, g.H, a.qbatch);
+  kern<<<grid, kAttnThreads, smem, st>>>(g, a, counters);
+  return ECCQ_OK;
+}
+// 1 = launched, 0 = geometry outside the tiled kernel (the warp-per-token kernel below serves it)
+template <typename TQ, int CODEC>
+static int try_prefill_tile(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  static const int env = [] { const char* v = std::getenv("ECCQ_PREFILL_TILE"); return v && *v ? std::atoi(v) : 1; }();
+  if (!env || g.H > 65535) return 0;
+  int rc;
+  if (g.D == 128) rc = launch_prefill_tile<TQ, CODEC, 4>(g, a, counters, st);
+  else if (g.D == 64) rc = launch_prefill_tile<TQ, CODEC, 2>(g, a, counters, st);
+  else if (g.D == 32) rc = launch_prefill_tile<TQ, CODEC, 1>(g, a, counters, st);
+  else return 0;
+  return rc ? rc : 1;
+}
+
 // ---- prefill (q_len > 1): the PREFILL instantiation of attn_partial_kernel, GP = queries per CTA
 template <typename TQ, int CODEC, int GP, int NCH>
 static int launch_prefill(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
@@ -396,6 +687,9 @@ static int launch_prefill(const CacheGeom& g, const AttnArgs& a, uint64_t* count
 }
 template <typename TQ, int CODEC>
 static int dispatch_prefill(const CacheGeom& g, const AttnArgs& a, uint64_t* counters, cudaStream_t st) {
+  const int took = try_prefill_tile<TQ, CODEC>(g, a, counters, st);
+  if (took < 0) return took;
+  if (took) return ECCQ_OK;
   const int per_chunk = CODEC == ECCQ_CODEC_GOLAY ? 96 : 128;
   const int nch = (g.D + per_chunk - 1) / per_chunk;
   if (nch > (CODEC == ECCQ_CODEC_GOLAY ? 3 : 2)) return fail(ECCQ_EUNSUPPORTED, "paged_prefill_attention: head_dim too large (max 256)");

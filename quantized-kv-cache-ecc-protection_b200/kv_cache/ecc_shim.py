@@ -30,11 +30,15 @@ from .._lib import (CTR_CORRECTED, CTR_DETECTED, CTR_FLIPPED, CTR_INTERPOLATED, 
                     device_of, load, new_counters, ptr, stream_of)
 from .attention_ecc import paged_attention_ecc, paged_prefill_attention_ecc, read_cache
 
-# Longest context / largest problem served by the fused causal prefill kernel (CUDA-core dot products: every token row is decoded
-# once per block of 8 queries, ~40 thread-instructions per (query, token) pair); beyond them the attention is GEMM-shaped and goes
-# through the fused read + the library's flash SDPA.  2^25 (query, token) pairs per layer call is ~1 ms on a B200.
+# Longest context / largest problem served by the fused causal prefill kernel (fp32 CUDA-core dot products, ~13 warp-instructions
+# per (query, token) pair); beyond them the attention is GEMM-shaped and goes through the fused read + the library's flash SDPA.
+# Measured on a B200 (layer call, Hamming(8,4)+interpolation, fp32 queries): GPT-2 geometry (12 x 64) 256 tokens 0.048 ms fused vs
+# 0.049 ms library, 1 024 tokens 0.22 vs 0.12 ms; LLaMA geometry (32 x 128, 8 kv-heads) 2 048 tokens 2.0 ms fused vs 2.8 ms library
+# (SDPA has no flash kernel for fp32 and the read materialises fp32 K/V).  Hence: up to 2^22 (query, token) pairs always, up to 2^27
+# for fp32 queries at head_dim >= 128.
 _PREFILL_FUSED_MAX_CTX = int(os.environ.get("ECCQ_PREFILL_FUSED_MAX_CTX", "2048"))
-_PREFILL_FUSED_MAX_PAIRS = int(os.environ.get("ECCQ_PREFILL_FUSED_MAX_PAIRS", str(1 << 25)))
+_PREFILL_FUSED_MAX_PAIRS = int(os.environ.get("ECCQ_PREFILL_FUSED_MAX_PAIRS", str(1 << 22)))
+_PREFILL_FUSED_MAX_PAIRS_F32 = int(os.environ.get("ECCQ_PREFILL_FUSED_MAX_PAIRS_F32", str(1 << 27)))
 
 
 def compute_injection_seed(base_seed: int, layer_idx: int, injection_count: int) -> int:
@@ -346,7 +350,9 @@ class ECCBackend:
             if shared:
                 out = out.reshape(self.num_kv_heads, B, G, D).permute(1, 0, 2, 3).reshape(B, Hq, D)
             return out.unsqueeze(2)
-        if max(lens) <= _PREFILL_FUSED_MAX_CTX and B * Hq * Sq * max(lens) <= _PREFILL_FUSED_MAX_PAIRS and D <= 256:
+        pairs = B * Hq * Sq * max(lens)
+        if max(lens) <= _PREFILL_FUSED_MAX_CTX and D <= 256 and (
+                pairs <= _PREFILL_FUSED_MAX_PAIRS or (q.dtype == torch.float32 and D >= 128 and pairs <= _PREFILL_FUSED_MAX_PAIRS_F32)):
             # ECC-fused causal prefill: ONE hand-written kernel consumes the codeword pages (decode + interpolation in the K/V
             # prologue, fp32 online softmax); no K/V tensor is materialised and no library attention kernel runs
             return paged_prefill_attention_ecc(q, m.k_cache, m.v_cache, bt, cl, m.k_scales, m.v_scales, layer_idx, m.block_size,

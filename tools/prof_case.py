@@ -2,7 +2,7 @@
 """Run ONE kernel variant of the hot path a few times (for ncu captures and quick timings).
 
     python tools/prof_case.py <case> [reps]
-    cases: copy h84enc h84dec write0 write3 write3lo read0 read1 readint4 writeg readg attn attni attng attn4   (C3 / C5 shapes)
+    cases: copy h84enc h84dec write0 write3 write3lo read0 read1 readint4 writeg readg attn attni attng attn4 prefill   (C3 / C5 shapes)
 Prints the median CUDA-event time and algorithmic GB/s when not under a profiler."""
 import statistics
 import sys
@@ -91,6 +91,19 @@ elif case.startswith(("write", "read")):
         interp = 1 if case == "read1" else 0
         timed(lambda: lib.eccq_cache_read(desc, P(m.block_table), S // BS, P(cl), B, S, 0, interp, _lib.ECCQ_F16, P(ko), P(vo), None, None, P(ctr), SP),
               vals * (cwb + 4 / D + 2))
+elif case == "prefill":     # ECC-fused causal prefill, GPT-2 small geometry (config 2 with 1 024-token texts): 12 heads x 64, MHA
+    from eccq_b200.kv_cache import paged_prefill_attention_ecc
+    Hh, Dh, Sq = 12, 64, 1024
+    nblk = Sq // BS
+    m = SimpleBlockManager(nblk, BS, 1, Hh, Dh, device=dev, codec="hamming84")
+    m.block_table = torch.randperm(nblk).to(torch.int32).view(1, nblk).to(dev)
+    kk = torch.randn(1, Sq, Hh * Dh, device=dev, dtype=torch.float16)
+    lib.eccq_cache_write(m.desc(), P(kk), P(kk.flip(1)), _lib.ECCQ_F16, P(m.block_table), nblk, None, 1, Sq, 0, _lib.INJECT_PHILOX_FAST,
+                         None, None, 1e-3, 1, 0, None, SP)
+    q = torch.randn(1, Hh, Sq, Dh, device=dev, dtype=torch.float32)
+    cl = torch.full((1,), Sq, dtype=torch.int32, device=dev)
+    timed(lambda: paged_prefill_attention_ecc(q, m.k_cache, m.v_cache, m.block_table, cl, m.k_scales, m.v_scales, 0, BS,
+                                              use_interpolation=True), 2 * Sq * Hh * Dh)
 else:
     Bq, ctx, HQ = 8, 32768, 32
     codec = "golay" if case == "attng" else "int4" if case == "attn4" else "hamming84"
