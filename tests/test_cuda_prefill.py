@@ -43,7 +43,7 @@ def ref_prefill(oracle, q, oc, bt, lens, layer, interp):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("codec,interp", [("hamming84", False), ("hamming84", True), ("hamming74", False), ("golay", False), ("int4", False)])
-@pytest.mark.parametrize("D,bs,Hq,Hkv", [(64, 16, 4, 4), (128, 16, 8, 2), (128, 32, 4, 1)])
+@pytest.mark.parametrize("D,bs,Hq,Hkv", [(64, 16, 4, 4), (128, 16, 8, 2), (128, 32, 4, 1), (32, 16, 6, 2), (96, 16, 4, 2)])   # 96: warp-per-token kernel
 def test_one_shot_prefill_matches_oracle(oracle, codec, interp, D, bs, Hq, Hkv):
     """ctx == Sq per batch row (the reference's case: top-left causal mask), ragged batch, flips at BER 0.02, counters counted once."""
     from eccq_b200.kv_cache import paged_prefill_attention_ecc
