@@ -421,14 +421,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_prefill_tile_kernel(CacheGe
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ctx = min(a.context_lens[i], a.max_blocks * g.bs);
   const int qstart = ctx - a.Sq;                   // query t sits at position qstart + t
-  const int row0 = blockIdx.x * kPfRows;           // first (position, head) row of this CTA inside the kv-head: row = pos * G + head
+  const int qblk = (int)gridDim.x - 1 - (int)blockIdx.x;   // the LAST query block sees the most tokens: it is scheduled first
+  const int row0 = qblk * kPfRows;                 // first (position, head) row of this CTA inside the kv-head: row = pos * G + head
   const int nrows = a.Sq * G;
   const int pos_last = min(a.Sq - 1, (row0 + kPfRows - 1) / G);
   const int tmax = max(0, min(ctx, qstart + pos_last + 1));   // tokens [0, tmax) are visible to some query of the CTA
   const int32_t* bt = a.block_table + (int64_t)i * a.max_blocks;
   const int rowbytes = GOLAY ? g.cw * 4 : D;
   const int64_t page_bytes = (int64_t)g.bs * rowbytes;
-  const bool do_count = a.count_errors && (int)blockIdx.x == (int)gridDim.x - 1 && (a.nseq > 1 || b == 0);
+  const bool do_count = a.count_errors && qblk == (int)gridDim.x - 1 && (a.nseq > 1 || b == 0);
   uint32_t ncorr = 0, ndet = 0;
 
   // ---- queries of the CTA -> shared memory
