@@ -421,18 +421,25 @@ __global__ void __launch_bounds__(kAttnThreads) attn_prefill_tile_kernel(CacheGe
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ctx = min(a.context_lens[i], a.max_blocks * g.bs);
   const int qstart = ctx - a.Sq;                   // query t sits at position qstart + t
-  const int qblk = (int)gridDim.x - 1 - (int)blockIdx.x;   // the LAST query block sees the most tokens: it is scheduled first
-  const int row0 = qblk * kPfRows;                 // first (position, head) row of this CTA inside the kv-head: row = pos * G + head
   const int nrows = a.Sq * G;
-  const int pos_last = min(a.Sq - 1, (row0 + kPfRows - 1) / G);
-  const int tmax = max(0, min(ctx, qstart + pos_last + 1));   // tokens [0, tmax) are visible to some query of the CTA
+  const int nqblk = (nrows + kPfRows - 1) / kPfRows;
   const int32_t* bt = a.block_table + (int64_t)i * a.max_blocks;
   const int rowbytes = GOLAY ? g.cw * 4 : D;
   const int64_t page_bytes = (int64_t)g.bs * rowbytes;
-  const bool do_count = a.count_errors && qblk == (int)gridDim.x - 1 && (a.nseq > 1 || b == 0);
   uint32_t ncorr = 0, ndet = 0;
+  // Causal load balance: a CTA takes query block n-1-x and then block x -- together always n+1 tiles of work -- instead of one block
+  // whose cost grows with its position (the last block's CTA used to run 32 x as long as the first one's and set the kernel time).
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+  const int qblk = pass == 0 ? nqblk - 1 - (int)blockIdx.x : (int)blockIdx.x;
+  if (pass == 1 && qblk >= nqblk - 1 - (int)blockIdx.x) break;   // odd count: the middle block was pass 0
+  if (pass == 1) __syncthreads();                  // every warp is done with the first block's queries in shared memory
+  const int row0 = qblk * kPfRows;                 // first (position, head) row of this block inside the kv-head: row = pos * G + head
+  const int pos_last = min(a.Sq - 1, (row0 + kPfRows - 1) / G);
+  const int tmax = max(0, min(ctx, qstart + pos_last + 1));   // tokens [0, tmax) are visible to some query of the CTA
+  const bool do_count = a.count_errors && qblk == nqblk - 1 && (a.nseq > 1 || b == 0);   // the last block sees every token
 
-  // ---- queries of the CTA -> shared memory
+  // ---- queries of the block -> shared memory
   for (int e = threadIdx.x; e < kPfRows * D; e += kAttnThreads) {
     const int r = e / D, d = e - r * D;
     const int rg = row0 + r;
@@ -637,6 +644,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_prefill_tile_kernel(CacheGe
 #pragma unroll
     for (int x = 0; x < DPL; ++x) orow[x] = Cvt<TQ>::to(acc[q][x] * inv);
   }
+  }   // pass
   if (a.count_errors) {
     const int idx[3] = {ECCQ_CTR_CORRECTED, ECCQ_CTR_DETECTED, ECCQ_CTR_INTERPOLATED};
     const uint32_t val[3] = {ncorr, ndet, a.interp ? ndet : 0u};
@@ -655,7 +663,8 @@ static int launch_prefill_tile(const CacheGeom& g, const AttnArgs& a, uint64_t* 
     if (e != cudaSuccess) return fail(ECCQ_ECUDA, cudaGetErrorString(e));
   }
   const int G = a.Hq / g.H;
-  dim3 grid((a.Sq * G + kPfRows - 1) / kPfRows, g.H, a.qbatch);
+  const int nqblk = (a.Sq * G + kPfRows - 1) / kPfRows;
+  dim3 grid((nqblk + 1) / 2, g.H, a.qbatch);      // a CTA takes query blocks n-1-x and x
   kern<<<grid, kAttnThreads, smem, st>>>(g, a, counters);
   return ECCQ_OK;
 }
