@@ -10,8 +10,22 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 SRC = HERE / "eccq_oracle.c"
-LIB = HERE / "_build" / "liboracle.so"
 _lib = None
+
+
+def _cpu_tag() -> str:
+    """The library is compiled with -march=native, and the build directory travels with the repository to other machines (the GPU
+    box): the file name carries a digest of this CPU's feature flags, so a host with different flags compiles its own copy instead
+    of loading code it may not be able to execute."""
+    import hashlib
+    try:
+        flags = next(line for line in open("/proc/cpuinfo") if line.startswith("flags"))
+    except (OSError, StopIteration):
+        flags = "unknown"
+    return hashlib.sha1(flags.encode()).hexdigest()[:10]
+
+
+LIB = HERE / "_build" / f"liboracle-{_cpu_tag()}.so"
 
 
 def build(force: bool = False) -> Path:
