@@ -392,8 +392,11 @@ static int run_attn(const CacheGeom& g, const AttnArgs& a_in, uint64_t* counters
 constexpr int kPfRows = 32;                        // query rows per CTA
 constexpr int kPfRPW = kPfRows / kAttnWarps;       // query rows per warp
 constexpr int kPfTile = 32;                        // tokens per tile (= lanes)
+#ifndef ECCQ_PF_MINBLOCKS
+#define ECCQ_PF_MINBLOCKS 2   // resident CTAs per SM the prefill tile kernel is compiled for (measured: 1 -> 0.28, 2 -> 0.20, 3 -> 0.21, 4 -> 0.24 ms on the GPT-2 1 024-token layer)
+#endif
 template <typename TQ, int CODEC, int DPL>
-__global__ void __launch_bounds__(kAttnThreads) attn_prefill_tile_kernel(CacheGeom g, AttnArgs a, uint64_t* counters) {
+__global__ void __launch_bounds__(kAttnThreads, ECCQ_PF_MINBLOCKS) attn_prefill_tile_kernel(CacheGeom g, AttnArgs a, uint64_t* counters) {
   constexpr bool GOLAY = CODEC == ECCQ_CODEC_GOLAY;
   constexpr int D = 32 * DPL;
   constexpr int KS = D + 4;                        // padded row stride (bytes) of the nibble tiles
